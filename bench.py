@@ -1,0 +1,391 @@
+#!/usr/bin/env python
+"""Complex-stage fwd+bwd throughput (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one pass of the complex stage over one batch of 64 synthetic NSynth-shaped clips per GPU
+(what reaches the stage is the encoder's logit vector, [64, 6195] ~ N(0,1), seed 511990): gate ->
+rectifier -> active sets -> embeddings -> 6 SCCN layers -> penalties, forward and backward, plus (N > 1)
+the NCCL all-reduce of the stage's parameter gradients.  Prints ONE JSON line on rank 0.
+
+--impl reference times the reference's CPU path for the same step (the oracle restatement: the
+reference itself cannot run end to end and needs absent third-party code) on the host
+cores, a bounded number of clips per step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+SEED = 511990                      # the reference's seed (encoder.py:91)
+METRIC = "complex_stage_fwd_bwd_samples_per_sec"
+UNIT = "samples/s"
+# SURVEY.md 8(d) / BASELINE.md 5: algorithmic HBM bytes per sample, default full complex, fwd+bwd
+SURVEY_BYTES_PER_SAMPLE_FULL = 121.2e6
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=64, help="clips per GPU per step")
+    ap.add_argument("--vertices", type=int, default=20)
+    ap.add_argument("--layers", type=int, default=6)
+    ap.add_argument("--channels", type=int, default=64)
+    ap.add_argument("--regime", default="full", choices=["full", "sparse"],
+                    help="full: shipped BinaryGumbel gate, every simplex active (the size SURVEY 8(d) is quoted on); "
+                         "sparse: Hard Concrete gate, exact zeros")
+    ap.add_argument("--cpu-samples", type=int, default=6, help="clips in the cpu_baseline sample")
+    ap.add_argument("--ref-clips-per-step", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-profile-pass", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def synthetic_inputs(batch, n_total, regime, rank):
+    g = torch.Generator().manual_seed(SEED + rank)
+    logits = torch.randn(batch, n_total, generator=g)
+    if regime == "full":      # Gumbel noise for the shipped gate: -log(Exp(1)), shape [2, B, N] (encoder.py:36)
+        noise = -torch.empty(2, batch, n_total).exponential_(generator=g).log()
+    else:                     # uniform noise for Hard Concrete
+        noise = torch.rand(batch, n_total, generator=g).clamp_(1e-6, 1 - 1e-6)
+    return logits, noise
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle chain, per clip in a Python loop exactly as the reference processes data
+# (batch size 1, trainer.py:93)
+# ------------------------------------------------------------------------------------------------
+class CpuReference:
+    def __init__(self, args):
+        from oracle import glue_oracle as glo, rectifier_oracle as ro
+        from oracle.sccn_oracle import OracleSCCN
+        torch.autograd.set_detect_anomaly(False)       # the reference switches it on at import; off when timing
+        torch.manual_seed(SEED)
+        self.args = args
+        self.n, self.C = args.vertices, args.channels
+        self.tab = ro.make_tables(self.n)
+        self.off = glo.rank_offsets(self.n)
+        self.sccn = OracleSCCN(self.C, 3, args.layers).train()
+        self.emb = []
+        for s in self.tab.sizes:
+            e = torch.nn.Embedding(max(s, 1), self.C)
+            ln = torch.nn.LayerNorm(self.C)
+            self.emb.append((e.weight, ln.weight, ln.bias))
+        self.vertex_bias = torch.ones(1) * 2.0
+        g = torch.Generator().manual_seed(SEED)
+        self.up = [torch.randn(s, self.C, generator=g) for s in self.tab.sizes]
+
+    def one_clip(self, logits, noise):
+        from oracle import gate_oracle as go, glue_oracle as glo
+        lc = logits.clone().requires_grad_(True)
+        if self.args.regime == "full":
+            z = go.binary_gumbel_train(lc, noise, 1.0)
+            res = glo.complex_from_probs(z, self.n, self.vertex_bias, self.tab, self.emb, True)
+        else:
+            loc = torch.relu(torch.tensor([2.0, 1.0, 1.0, 1.5]))
+            z = go.hard_concrete(lc, noise, 2.0 / 3.0, -0.1, 1.1, loc, self.off)
+            res = glo.complex_from_probs(z, self.n, self.vertex_bias, self.tab, self.emb, False)
+        if res is None:
+            return
+        emb, (adj, inc), rect = res
+        out = self.sccn({f"rank_{r}": emb[f"rank_{r}"] for r in range(4)}, inc, adj)
+        names = ("vertices", "edges", "triangles", "tetra")
+        outs = [out[f"rank_{r}"] for r in range(4)]
+        ups = [self.up[r][emb["active_indices"][names[r]]] for r in range(4)]
+        vp = glo.vertex_penalty(rect[0], 8, 16)
+        ent = glo.entropy_loss(*rect)
+        torch.autograd.backward(outs + [vp, ent], ups + [torch.ones(()), torch.ones(())])
+
+    def time_clips(self, n_clips, seed_rank=0):
+        logits, noise = synthetic_inputs(max(n_clips, 1), self.off[4], self.args.regime, seed_rank)
+        t0 = time.perf_counter()
+        for b in range(n_clips):
+            self.one_clip(logits[b], noise[:, b] if self.args.regime == "full" else noise[b])
+        return time.perf_counter() - t0
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    ref = CpuReference(args)
+    per = args.ref_clips_per_step
+    for _ in range(args.warmup):
+        ref.time_clips(per)
+    t = sum(ref.time_clips(per) for _ in range(args.steps))
+    value = per * args.steps / t
+    cores = torch.get_num_threads()
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, per),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{per} clips per step x {args.steps} steps, per-clip Python loop as trainer.py:93; "
+                                   f"os.cpu_count()={os.cpu_count()}"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, batch):
+    return {"workload": f"complex stage fwd+bwd: {args.vertices} vertices (6195 candidate simplices), C={args.channels}, "
+                        f"{args.layers} SCCN layers, regime={args.regime}",
+            "clips_per_gpu_per_step": batch, "clip": "4 s @ 16 kHz NSynth-shaped (enters the stage as a [6195] logit vector)",
+            "gate": "BinaryGumbel (shipped, encoder.py:26-53)" if args.regime == "full" else "HardConcrete (builder's spec)",
+            "parallelism": f"dp{args.gpus} (batch-sharded, gradient all-reduce)"}
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index):
+        self.file = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(device_index)], stdout=self.file, stderr=subprocess.DEVNULL)
+        except OSError:
+            pass
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        self.file.flush()
+        self.file.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for row in self.file.read().splitlines():
+            f = [c.strip() for c in row.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        os.unlink(self.file.name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def algorithmic_bytes_per_call(name, counts, ch, n_layers):
+    """Compulsory HBM bytes of one call of a hot entry point, averaged over the ranks it is launched
+    for (DESIGN.md "Kernels and their byte counts").  counts = live rows per rank over the batch."""
+    k_msgs = [2, 3, 3, 2]
+    rows = sum(counts)
+    k_rows = sum(k * c for k, c in zip(k_msgs, counts))
+    row_b = 4 * ch
+    per_layer = {
+        "topo_sccn_combine_fwd": (k_rows + 2 * rows) * row_b,
+        "topo_sccn_combine_bwd_attention": (2 * k_rows + 3 * rows) * row_b,
+        "topo_sccn_combine_bwd_conv": 3 * k_rows * row_b,
+        "topo_sccn_aggregate_fwd": (rows + k_rows) * row_b,
+        "topo_sccn_aggregate_bwd": (3 * rows + k_rows + 2 * (counts[2] * 2 + counts[3])) * row_b,
+    }
+    calls_per_layer = {"topo_sccn_combine_fwd": 4, "topo_sccn_combine_bwd_attention": 4, "topo_sccn_combine_bwd_conv": 4,
+                       "topo_sccn_aggregate_fwd": 1, "topo_sccn_aggregate_bwd": 1}
+    if name not in per_layer:
+        return None
+    return per_layer[name] / calls_per_layer[name]
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    import topo_audio_autoencoder_b200 as T
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a CUDA device: there is no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+
+    torch.manual_seed(SEED)     # identical replicas on every rank
+    kw = dict(gate="binary_gumbel", bias_on="probs") if args.regime == "full" else dict(gate="hard_concrete", bias_on="logits")
+    stage = T.ComplexStage(args.vertices, channels=args.channels, n_layers=args.layers, **kw).to(dev).train()
+    params = [p for p in stage.parameters() if p.requires_grad]
+    n_total = stage.head.total_simplices
+    B = args.batch
+
+    logits_h, noise_h = synthetic_inputs(B, n_total, args.regime, rank)
+    logits_pin, noise_pin = logits_h.pin_memory(), noise_h.pin_memory()
+    logits_d, noise_d = logits_h.to(dev), noise_h.to(dev)
+    g = torch.Generator().manual_seed(SEED)
+    counts_max = stage.head._tables.counts
+    ups = [torch.randn(B * c, args.channels, generator=g).to(dev) for c in counts_max]   # the decoder's gradient
+    ones = torch.ones(B, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def step(lg, nz):
+        for p in params:
+            p.grad = None
+        lg = lg.detach().requires_grad_(True)
+        out = stage(lg, nz)
+        outs = [out[f"rank_{r}"] for r in range(4)]
+        torch.autograd.backward(outs + [out["vertex_penalty"], out["entropy_loss"]], ups + [ones, ones])
+        if world > 1:
+            flat = torch.cat([p.grad.reshape(-1) for p in params])
+            dist.all_reduce(flat)
+            flat.div_(world)
+            o = 0
+            for p in params:
+                p.grad.copy_(flat[o:o + p.numel()].view_as(p.grad))
+                o += p.numel()
+        return out, lg
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(k, host_io):
+        """k steps, each bracketed by its own event pair; L2 is flushed between steps outside the pairs."""
+        evs = []
+        barrier()
+        for _ in range(k):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            if host_io:
+                lg = logits_pin.to(dev, non_blocking=True)
+                nz = noise_pin.to(dev, non_blocking=True)
+                out, lg = step(lg, nz)
+                res = torch.cat([out["vertex_penalty"], out["entropy_loss"], lg.grad.sum().reshape(1)]).cpu()
+            else:
+                step(logits_d, noise_d)
+            e1.record()
+            evs.append((e0, e1))
+        barrier()
+        ms = sum(a.elapsed_time(b) for a, b in evs)
+        t = torch.tensor([ms], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
+    # ---- warm-up, then the timed regions ----
+    for _ in range(max(args.warmup, 3)):
+        step(logits_d, noise_d)
+    T.lib.reset_counts()
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms = timed(args.steps, host_io=False)
+    launches = T.lib.kernel_launches()
+    clocks = sampler.stop() if sampler else None
+    for _ in range(2):
+        timed(1, host_io=True)
+    ms_e2e = timed(args.steps, host_io=True)
+
+    value = world * B * args.steps / (ms * 1e-3)
+    e2e_value = world * B * args.steps / (ms_e2e * 1e-3)
+
+    # ---- per-entry-point device time: one profile pass with CUDA events on the launch stream ----
+    roofline, breakdown = None, None
+    hbm_peak, peak_src = peaks()
+    out, _ = step(logits_d, noise_d)
+    live = out["complex"].row_off[:, B].tolist()
+    if rank == 0 and not args.no_profile_pass:
+        passes = 3
+        T.lib.start_timing()
+        for _ in range(passes):
+            flush.zero_()
+            step(logits_d, noise_d)
+        stats = T.lib.stop_timing()
+        total = sum(v[1] for v in stats.values())
+        breakdown = {k: {"calls_per_step": v[0] // passes, "ms_per_step": v[1] / passes, "share": v[1] / total}
+                     for k, v in sorted(stats.items(), key=lambda kv: -kv[1][1])}
+        top = next(iter(breakdown))
+        calls, tot_ms = stats[top]
+        per_call = algorithmic_bytes_per_call(top, live, args.channels, args.layers)
+        if per_call is not None:
+            achieved = per_call / (tot_ms / calls * 1e-3) / 1e9
+            roofline = {"kernel": top, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                        "algorithmic_bytes_per_launch": per_call, "avg_launch_ms": tot_ms / calls,
+                        "share_of_step": breakdown[top]["share"]}
+    stage_bytes = SURVEY_BYTES_PER_SAMPLE_FULL if args.regime == "full" and args.vertices == 20 and args.layers == 6 else None
+    roofline_stage = None
+    if stage_bytes:
+        ach = stage_bytes * value / world / 1e9
+        roofline_stage = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                          "bytes_per_sample": stage_bytes, "frac_of_nominal_8TBs": ach / 8000.0, "per": "GPU",
+                          "note": "SURVEY.md 8(d) algorithmic bytes per sample x samples/s per GPU"}
+
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        ref = CpuReference(args)
+        ref.time_clips(1)
+        t = ref.time_clips(args.cpu_samples)
+        cpu = {"value": args.cpu_samples / t, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+               "sample": f"{args.cpu_samples} clips of the same workload, per-clip loop (oracle chain: rectify + dense "
+                         f"operator build + SCCN x{args.layers}, fwd+bwd); os.cpu_count()={os.cpu_count()}"}
+
+    if rank == 0:
+        h2d = logits_pin.numel() * 4 + noise_pin.numel() * 4
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": dict(workload_config(args, B), live_rows_per_rank=live,
+                           l2="flushed between steps (256 MiB write) outside the per-step event pairs; "
+                              "the step's working set (~GBs of saved activations) also exceeds the 126 MB L2"),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": (2 * B + 1) * 4,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "roofline_stage": roofline_stage,
+            "cpu_baseline": cpu, "breakdown": breakdown,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

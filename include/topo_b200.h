@@ -1,0 +1,291 @@
+/*
+ * topo_b200.h -- C ABI of the B200-native simplicial-complex stage.
+ *
+ * One shared library (libtopo_b200.so, built by topo_audio_autoencoder_b200/csrc/build.py with
+ * nvcc -gencode arch=compute_100a,code=sm_100a).  Plain pointers and sizes only; no torch types.
+ * The reference (Monlarc/topo-audio-autoencoder) is pure Python and has no FFI layer, so each
+ * entry point cites the Python function whose arithmetic it replaces; INTEGRATION.md shows the
+ * ctypes binding that puts it behind the reference's own signatures.
+ *
+ * Conventions
+ *   - every pointer named dev_* / without a host_ prefix is DEVICE memory on the current device;
+ *     host_* pointers are host memory.
+ *   - outputs are caller-allocated; entry points neither allocate nor synchronise (the two
+ *     topo_tables_* constructors/destructors excepted) and enqueue on `stream`.
+ *   - return value: TOPO_OK or an error code; topo_last_error() gives a thread-local message.
+ *   - all floating point is fp32 (IEEE, denormals kept: the sparsity pattern of the reference's
+ *     operators is "whatever is non-zero in fp32", complex_builder.py:82-85).
+ *
+ * Layout of one batch of complexes ("simplex axis")
+ *   A complex on n vertices has n_r = C(n, r+1) candidate simplices of rank r = 0..3, listed in
+ *   itertools.combinations (lexicographic) order (rectifier.py:28-30).  Per sample all ranks share
+ *   one axis of length N = n_0+n_1+n_2+n_3 with rank r in [off_r, off_r + n_r).  A batch is a
+ *   row-major [B, N] array.  Feature matrices are COMPACT: rank r holds only the active simplices
+ *   of every sample, samples concatenated, rows in ascending simplex id -- exactly the row order
+ *   of the reference's per-sample [n_r_active, C] tensors (encoder.py:230-247).
+ */
+#ifndef TOPO_B200_H
+#define TOPO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TOPO_OK 0
+#define TOPO_ERR_INVALID 1      /* bad argument */
+#define TOPO_ERR_CUDA 2         /* CUDA runtime error (message in topo_last_error) */
+#define TOPO_ERR_UNSUPPORTED 3  /* valid request outside what the kernels are instantiated for */
+
+typedef void* topo_stream_t;            /* a cudaStream_t */
+typedef struct topo_tables topo_tables; /* opaque: static combinatorial tables of one n, on one device */
+
+int topo_version(void);
+const char* topo_last_error(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * T1. Constraint tables.   Replaces ConstraintMatrices.create(n)  (rectifier.py:24-64).
+ * Built on the host with closed-form lexicographic rank/unrank (no linear searches) and
+ * uploaded once.  Holds: vertex lists, face ids, coface ids and sorted adjacency neighbour lists.
+ * ------------------------------------------------------------------------------------------- */
+int topo_tables_create(int n_vertices, topo_tables** out);
+/* upload_to_device == 0 builds the host tables only (no CUDA call; for inspection and CPU tests) */
+int topo_tables_create_ex(int n_vertices, int upload_to_device, topo_tables** out);
+void topo_tables_destroy(topo_tables* t);
+/* counts[r] = n_r; offsets[r] = off_r (5 entries, offsets[4] = N) */
+int topo_tables_sizes(const topo_tables* t, int64_t host_counts[4], int64_t host_offsets[5]);
+/* [n_r, r+1] int64 vertex ids of every rank-r simplex == SimplexIndices.{edges,triangles,tetra} */
+int topo_tables_simplex_vertices(const topo_tables* t, int rank, int64_t* host_out);
+/* [n_r, r+1] int32 ids (within rank r-1) of the faces of every rank-r simplex, ascending; rank>=1 */
+int topo_tables_faces(const topo_tables* t, int rank, int32_t* host_out);
+/* [n_r, n-1-r] int32 ids (within rank r+1) of the cofaces of every rank-r simplex, ascending; rank<=2 */
+int topo_tables_cofaces(const topo_tables* t, int rank, int32_t* host_out);
+/* dense 0/1 [n_r, n_{r-1}] fp32 == vertex_to_edge / edge_to_triangle / triangle_to_tetra */
+int topo_tables_face_matrix(const topo_tables* t, int rank, float* dev_out, topo_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * G1. Gates.
+ * Hard Concrete (README.md:15-18 names it; the reference ships no code -- spec in DESIGN.md):
+ *   x = logits + loc[rank];  training: x = (log u - log(1-u) + x) / beta
+ *   s = sigmoid(x);  z = clamp(s*(zeta-gamma)+gamma, 0, 1);  ste: value (z > 0.5), gradient of z
+ * params = device float[7] {beta, gamma, zeta, loc0, loc1, loc2, loc3}.  128-bit vectorised.
+ * grad_params (device float[7]) is overwritten.  u may be NULL when training == 0.
+ * Binary Gumbel: BinaryGumbel.forward training branch (encoder.py:34-41),
+ *   softmax(([l, 1-l] + g) / temp, dim 0)[0] with g = dev_gumbels [2, count].
+ * ------------------------------------------------------------------------------------------- */
+int topo_hard_concrete_fwd(const float* logits, const float* u, const float* params,
+                           const int64_t host_offsets[5], int64_t batch, int training, int ste,
+                           float* z, topo_stream_t stream);
+int topo_hard_concrete_bwd(const float* logits, const float* u, const float* params,
+                           const int64_t host_offsets[5], int64_t batch, int training,
+                           const float* grad_z, float* grad_logits, float* grad_params,
+                           topo_stream_t stream);
+int topo_binary_gumbel_fwd(const float* logits, const float* gumbels, float temp, int64_t count,
+                           float* probs, topo_stream_t stream);
+int topo_binary_gumbel_bwd(const float* logits, const float* gumbels, float temp, int64_t count,
+                           const float* grad_probs, float* grad_logits, topo_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * R2. Geometric-mean face rectifier.   Replaces enforce_constraints  (rectifier.py:75-127).
+ *   c_s = exp(sum_{f face of s} log(p'_f + eps) / (r+1)), forced to exact 0 when any face is 0;
+ *   p'_s = min(p_s, c_s), level by level on the rectified level below.
+ * Backward follows torch autograd of that expression, including torch.minimum's 50/50 split on
+ * ties and the zero gradient path of the masked branch.  workspace: [batch, N] floats.
+ * ------------------------------------------------------------------------------------------- */
+int topo_rectify_fwd(const topo_tables* t, const float* probs_in, float eps, int64_t batch,
+                     float* probs_out, topo_stream_t stream);
+int topo_rectify_bwd(const topo_tables* t, const float* probs_in, const float* probs_out,
+                     const float* grad_out, float eps, int64_t batch, float* grad_in,
+                     float* workspace, topo_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * G3. Active sets.   Replaces the four nonzero() calls of get_active_simplex_embeddings
+ * (encoder.py:230-233) for a whole batch.
+ *   pos     [B, N] int32: position of the simplex in its sample's ascending active list, or -1
+ *   act_idx [B, N] int32: act_idx[b, off_r + i] = id (within rank r) of the i-th active simplex
+ *   counts  [B, 4] int32
+ *   row_off [4, B+1] int32: exclusive scan of counts over the batch (compact row of sample b
+ *           rank r starts at row_off[r][b]; row_off[r][B] = total active rows of rank r)
+ * ------------------------------------------------------------------------------------------- */
+int topo_active_sets(const topo_tables* t, const float* probs, int64_t batch, int32_t* pos,
+                     int32_t* act_idx, int32_t* counts, int32_t* row_off, topo_stream_t stream);
+
+/* A batch of complexes as the SCCN / embedding / operator kernels see it (device pointers). */
+typedef struct {
+    const float* probs;      /* [B, N] rectified probabilities */
+    const int32_t* pos;      /* [B, N] */
+    const int32_t* act_idx;  /* [B, N] */
+    const int32_t* counts;   /* [B, 4] */
+    const int32_t* row_off;  /* [4, B+1] */
+    int64_t batch;
+} topo_complex_view;
+
+/* ---------------------------------------------------------------------------------------------
+ * L1 / L2. Structural penalties.  compute_vertex_penalty (encoder.py:199-203) and
+ * compute_entropy_loss (encoder.py:205-221; line 223 raises in the reference and is omitted).
+ * One value per sample.
+ * ------------------------------------------------------------------------------------------- */
+int topo_penalties_fwd(const topo_tables* t, const float* probs, int64_t batch, float min_active,
+                       float max_active, float* vertex_penalty, float* entropy_loss,
+                       topo_stream_t stream);
+int topo_penalties_bwd(const topo_tables* t, const float* probs, int64_t batch, float min_active,
+                       float max_active, const float* grad_vertex_penalty,
+                       const float* grad_entropy_loss, float* grad_probs, topo_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * G3 (cont). Active embeddings:  X_r[row] = lne_r[id] * p[id]   (encoder.py:242-247), where
+ * lne_r = LayerNorm(Embedding table) is computed once per step with topo_layernorm_fwd.
+ * bwd: grad_probs[b, off_r+id] += <g, lne[id]>;  grad_lne[id] = sum_b p * g  (overwritten).
+ * ------------------------------------------------------------------------------------------- */
+int topo_embed_fwd(const topo_tables* t, const topo_complex_view* cv, int rank, int channels,
+                   const float* lne, float* x_out, topo_stream_t stream);
+int topo_embed_bwd(const topo_tables* t, const topo_complex_view* cv, int rank, int channels,
+                   const float* lne, const float* grad_x, float* grad_lne, float* grad_probs,
+                   topo_stream_t stream);
+
+/* Row-wise LayerNorm over [rows, channels] (nn.LayerNorm, eps inside the sqrt, biased variance).
+ * bwd overwrites grad_x and ACCUMULATES into grad_gamma / grad_beta. */
+int topo_layernorm_fwd(int64_t rows, int channels, const float* x, const float* gamma,
+                       const float* beta, float eps, float* y, topo_stream_t stream);
+int topo_layernorm_bwd(int64_t rows, int channels, const float* x, const float* gamma, float eps,
+                       const float* grad_y, float* grad_x, float* grad_gamma, float* grad_beta,
+                       topo_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * B2. Weighted incidence / adjacency operators.  Replaces build_sparse_matrices
+ * (complex_builder.py:23-115) for ONE sample.  op: 0..3 = adjacency rank_0..rank_3,
+ * 4..6 = incidence rank_1..rank_3.  Active sets come from the caller (pos/act_idx/counts of one
+ * sample, as produced by topo_active_sets or derived from user index lists).
+ *   count: row_nnz[op][i] for every compact row          -> dev_row_nnz  [7, max_rows]
+ *   scan : exclusive scan per operator                   -> dev_row_ptr  [7, max_rows + 1]
+ *   fill : COO (row-major sorted) int64 indices + values -> per-operator caller buffers
+ *   bwd  : grad_probs[N] += d(values)/d(probs) . grad_values
+ * Values are single fp32 products (p_e | p_t*p_t | p_s*p_s | p_s*p_s' | p_coface), so they are
+ * bit-identical to the reference's dense products; an entry exists iff its value != 0.
+ * ------------------------------------------------------------------------------------------- */
+int topo_operators_count(const topo_tables* t, const float* probs, const int32_t* pos,
+                         const int32_t* act_idx, const int32_t* counts, int64_t max_rows,
+                         int32_t* row_ptr /* [7, max_rows+1] */, topo_stream_t stream);
+int topo_operators_fill(const topo_tables* t, const float* probs, const int32_t* pos,
+                        const int32_t* act_idx, const int32_t* counts, int64_t max_rows,
+                        const int32_t* row_ptr, int64_t* const dev_rows[7], int64_t* const dev_cols[7],
+                        float* const dev_vals[7], topo_stream_t stream);
+int topo_operators_bwd(const topo_tables* t, const float* probs, const int32_t* pos,
+                       const int32_t* act_idx, const int32_t* counts, int64_t max_rows,
+                       const int32_t* row_ptr, const float* const dev_grad_vals[7],
+                       float* grad_probs, topo_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * S1 (a). Matrix-free neighbourhood aggregation for a whole batch -- the SpMM half of
+ * convs_*(x_source, neighborhood) (custom_sccn.py:78-81, 95-98, 113-116), using
+ * N @ (X @ W) == (N @ X) @ W and the factorisation of every adjacency through the incidences
+ * (complex_builder.py:62-64):
+ *   down[r] = I_{r+1} X_{r+1}          r = 0..2   (rows: rank r)      "from above"
+ *   up[r]   = I_r^T  X_{r-1}           r = 1..3   (rows: rank r)      "from below"
+ *   same[0] = A_0 X_0
+ *   same[1] = I_2 up[2] - diag.,  same[2] = I_3 up[3] - diag.,  same[3] = I_3^T down[2] - diag.
+ * No operator is materialised: neighbours come from the static tables, weights from probs.
+ * x / down / up / same: arrays of per-rank compact [rows_r, channels] device pointers
+ * (down[3] and up[0] unused, may be NULL).
+ * bwd: g_down / g_up / g_same are the gradients w.r.t. the aggregates (g_down[2], g_up[2],
+ * g_up[3] are updated in place to their totals); g_x is ACCUMULATED (+=), g_probs [B, N] too.
+ * ------------------------------------------------------------------------------------------- */
+int topo_sccn_aggregate_fwd(const topo_tables* t, const topo_complex_view* cv, int channels,
+                            const float* const x[4], float* const down[4], float* const up[4],
+                            float* const same[4], topo_stream_t stream);
+int topo_sccn_aggregate_bwd(const topo_tables* t, const topo_complex_view* cv, int channels,
+                            const float* const x[4], const float* const down[4],
+                            const float* const up[4], float* const g_down[4], float* const g_up[4],
+                            const float* const g_same[4], float* const g_x[4], float* g_probs,
+                            topo_stream_t stream);
+
+/* Generic CSR path for caller-supplied sparse operators (GradientSCCN.forward accepts arbitrary
+ * matrices, test_sccn.py:15-35):  y = A x;  g_val[e] = <g_y[row(e)], x[col(e)]>. */
+int topo_spmm_csr(int64_t rows, const int32_t* row_ptr, const int32_t* col_idx, const float* vals,
+                  const float* x, int channels, float* y, topo_stream_t stream);
+int topo_sddmm_csr(int64_t rows, const int32_t* row_ptr, const int32_t* col_idx, const float* g_y,
+                   const float* x, int channels, float* g_vals, topo_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * S1 (b). Message combine for one rank -- the dense half of GradientSCCNLayer.forward
+ * (custom_sccn.py:73-136) on a tile of target rows, fused in one kernel:
+ *   m_k  = scale_k * (agg_k @ W_k) + x                    (conv weight, scale, residual)
+ *   a    = softmax_k( Linear2(GELU(Linear1(m_k))) )       (message attention, :128-130)
+ *   out  = sum_k a_k m_k;  out = LayerNorm(out) if apply_ln (:132-134)
+ * n_msgs in 1..3.  n_rows_dev (nullable) is a device int32 holding the live row count
+ * (<= rows); rows past it are not touched.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    int channels;
+    int n_msgs;
+    const float* agg[3];     /* [rows, C] aggregate per message */
+    const float* w[3];       /* [C, C] conv weight (in, out) per message */
+    const float* scale[3];   /* device scalar per message */
+    const float* x;          /* [rows, C] current features (residual); NULL when residual is off */
+    const float* att_w1;     /* [C, C]  nn.Linear(C, C).weight  (out, in) */
+    const float* att_b1;     /* [C] */
+    const float* att_w2;     /* [C]     nn.Linear(C, 1).weight */
+    const float* att_b2;     /* [1] */
+    const float* ln_gamma;   /* [C] */
+    const float* ln_beta;    /* [C] */
+    float ln_eps;
+    int apply_ln;
+} topo_combine_params;
+
+typedef struct {
+    float* g_agg[3];         /* [rows, C] overwritten */
+    float* g_x;              /* [rows, C] overwritten (residual path only) */
+    float* g_wprod[3];       /* [C, C] ACCUMULATED: agg_k^T (dL/dm_k); dW_k = scale_k * this,
+                                dscale_k = <W_k, this> (finished by the caller, 2 tiny ops) */
+    float* g_att_w1;         /* ACCUMULATED */
+    float* g_att_b1;
+    float* g_att_w2;
+    float* g_att_b2;
+    float* g_ln_gamma;
+    float* g_ln_beta;
+} topo_combine_grads;
+
+int topo_sccn_combine_fwd(const topo_combine_params* p, int64_t rows, const int32_t* n_rows_dev,
+                          float* out, topo_stream_t stream);
+/* workspace: n_msgs * rows * C floats (dL/dm_k between the two backward kernels).
+ * _attention: LayerNorm, softmax and attention-MLP backward -> dL/dm_k (workspace), g_x, attention and
+ *             LayerNorm parameter gradients.  _conv: dL/dagg_k and g_wprod from the workspace.
+ * topo_sccn_combine_bwd runs both. */
+int topo_sccn_combine_bwd_attention(const topo_combine_params* p, int64_t rows,
+                                    const int32_t* n_rows_dev, const float* grad_out,
+                                    const topo_combine_grads* g, float* workspace,
+                                    topo_stream_t stream);
+int topo_sccn_combine_bwd_conv(const topo_combine_params* p, int64_t rows, const int32_t* n_rows_dev,
+                               const topo_combine_grads* g, const float* workspace,
+                               topo_stream_t stream);
+int topo_sccn_combine_bwd(const topo_combine_params* p, int64_t rows, const int32_t* n_rows_dev,
+                          const float* grad_out, const topo_combine_grads* g, float* workspace,
+                          topo_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * D1-D3. Tiled pairwise spectral distance.  Replaces the pair loop of compute_distances
+ * (precompute_distances.py:89-115) and BatchAudioDistance.forward (:33-49) on precomputed
+ * magnitude spectrograms:  spec [n, d], d = sum of the n_scales segment lengths (one segment per
+ * STFT scale, flattened),
+ *   d(i,j) = sum_s [ mean((x_s-y_s)^2) / (mean(x_s^2) + 1e-7) + mean|log(x_s+eps) - log(y_s+eps)| ]
+ * with x = the LOWER-index clip (so the normaliser comes from it, :89, :106-110), mirrored
+ * (:114-115), zero diagonal.
+ *   padded_size: row length Dp after every segment is padded to a multiple of 16 bins
+ *   prepare    : spec -> spec_p [n, Dp] (zero padded), logspec_p = log(spec + eps) (0 in the padding),
+ *                sq_mean [n, n_scales] = mean of squares per clip and scale
+ *   rows       : the block [row_begin, row_end) x [col_begin, col_end) of the symmetric matrix
+ *                (row-block sharding across ranks needs no collective)
+ * ------------------------------------------------------------------------------------------- */
+int64_t topo_distance_padded_size(const int64_t* host_seg_len, int n_scales);
+int topo_distance_prepare(const float* spec, int64_t n, int64_t d, const int64_t* host_seg_len,
+                          int n_scales, float log_eps, float* spec_p, float* logspec_p,
+                          float* sq_mean, topo_stream_t stream);
+int topo_distance_rows(const float* spec_p, const float* logspec_p, const float* sq_mean, int64_t n,
+                       const int64_t* host_seg_len, int n_scales, int64_t row_begin, int64_t row_end,
+                       int64_t col_begin, int64_t col_end, float* out, topo_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TOPO_B200_H */

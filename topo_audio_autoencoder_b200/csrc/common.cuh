@@ -1,0 +1,123 @@
+// Shared helpers for the topo_b200 kernels (sm_100a).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "topo_b200.h"
+
+namespace topo {
+
+void set_error(const std::string& msg);
+
+#define TOPO_REQUIRE(cond, msg)                                        \
+    do {                                                               \
+        if (!(cond)) {                                                 \
+            ::topo::set_error(std::string(__func__) + ": " + (msg));   \
+            return TOPO_ERR_INVALID;                                   \
+        }                                                              \
+    } while (0)
+
+#define TOPO_CUDA(expr)                                                                 \
+    do {                                                                                \
+        cudaError_t err__ = (expr);                                                     \
+        if (err__ != cudaSuccess) {                                                     \
+            ::topo::set_error(std::string(__func__) + ": " + cudaGetErrorString(err__)); \
+            return TOPO_ERR_CUDA;                                                       \
+        }                                                                               \
+    } while (0)
+
+#define TOPO_LAUNCH_CHECK() TOPO_CUDA(cudaGetLastError())
+
+static inline cudaStream_t as_stream(topo_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+int sm_count();
+
+constexpr int kMaxRank = 3;
+
+// Device-resident static tables of one vertex count.  All ids are int32 and local to their rank.
+struct DeviceTables {
+    int n;                 // vertices
+    int cnt[4];            // n_r
+    int off[5];            // rank offsets on the simplex axis
+    int ncof[3];           // cofaces per simplex of rank r: n-1-r
+    const int* faces[4];   // faces[r]: [n_r][r+1] ids in rank r-1 (r>=1); faces[0] = nullptr
+    const int* cofaces[3]; // cofaces[r]: [n_r][ncof[r]] ids in rank r+1, ascending
+    // explicit adjacency neighbour lists, sorted by neighbour id (operator builder only)
+    int adj_w[4];          // slots per row: n-1, 2(n-2), 3(n-3), 4(n-4)
+    const int* adj_nbr[4]; // [n_r][adj_w[r]] neighbour id in rank r
+    const int* adj_via[4]; // [n_r][adj_w[r]] id of the simplex the pair shares (edge | coface | coface | face)
+};
+
+}  // namespace topo
+
+struct topo_tables {
+    topo::DeviceTables d;                 // device pointers
+    int device;
+    std::vector<int64_t> h_verts[4];      // [n_r][r+1] vertex ids (host)
+    std::vector<int> h_faces[4];          // [n_r][r+1] (host)
+    std::vector<int> h_cofaces[3];        // [n_r][n-1-r] (host)
+    std::vector<void*> dev_blocks;        // everything cudaMalloc'ed for this object
+};
+
+namespace topo {
+
+// ---- device helpers ----
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// sum over the 16 lanes that share (lane >> 4)
+__device__ __forceinline__ float half_warp_sum(float v) {
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ float gelu_exact(float x) {
+    return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+// d/dx [0.5 x (1 + erf(x/sqrt2))] = 0.5 (1 + erf(x/sqrt2)) + x * exp(-x^2/2) / sqrt(2 pi)
+__device__ __forceinline__ float gelu_exact_grad(float x) {
+    const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+    const float pdf = 0.39894228040143267794f * expf(-0.5f * x * x);
+    return cdf + x * pdf;
+}
+
+template <int VEC>
+struct Vec;
+template <>
+struct Vec<1> {
+    float v[1];
+    __device__ __forceinline__ void load(const float* p) { v[0] = __ldg(p); }
+    __device__ __forceinline__ void store(float* p) const { p[0] = v[0]; }
+};
+template <>
+struct Vec<2> {
+    float v[2];
+    __device__ __forceinline__ void load(const float* p) {
+        const float2 t = __ldg(reinterpret_cast<const float2*>(p));
+        v[0] = t.x; v[1] = t.y;
+    }
+    __device__ __forceinline__ void store(float* p) const {
+        *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]);
+    }
+};
+template <>
+struct Vec<4> {
+    float v[4];
+    __device__ __forceinline__ void load(const float* p) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    }
+    __device__ __forceinline__ void store(float* p) const {
+        *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+};
+
+}  // namespace topo

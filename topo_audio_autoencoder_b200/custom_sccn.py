@@ -1,0 +1,365 @@
+"""Drop-in for the reference's ``custom_sccn.py`` (GradientSCCNLayer / GradientSCCN).
+
+Reference: custom_sccn.py:7-162.  Same constructor signatures, parameter names (state-dict
+compatible: ``convs_same_rank.rank_r.weight`` ...), dict-in / dict-out forward, and the same
+"missing rank -> skipped" rules (custom_sccn.py:69-71, 123-125).
+
+Two execution paths, both through libtopo_b200:
+  * ``forward(features, incidences, adjacencies)``: caller-supplied sparse COO operators (any
+    pattern, as in the reference's test_sccn.py) -> CSR SpMM / SDDMM kernels + fused combine.
+  * ``forward_complex(batch, features)``: a whole batch of complexes described by their
+    rectified probabilities; neighbourhoods are walked matrix-free (csrc/aggregate.cu).
+
+The base classes of the reference (TopoModelX ``SCCNLayer`` / ``SCCN`` / ``Conv``) are not on
+this machine; ``Conv`` here is the published contract: ``neighborhood @ (x_source @ weight)``,
+weight [in, out], Xavier-uniform gain 1.414.  The kernels evaluate it as
+``(neighborhood @ x_source) @ weight``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._lib import lib, check, ptr, ptr_array, stream, ComplexView, CombineParams, CombineGrads
+from .rectifier import _Tables
+
+
+# --------------------------------------------------------------------------------------------
+# generic sparse operators
+# --------------------------------------------------------------------------------------------
+class CsrPattern:
+    """int32 CSR of a coalesced COO pattern, plus the CSR of its transpose and the entry
+    permutation between the two (index plumbing, done once per operator per forward)."""
+
+    def __init__(self, indices: torch.Tensor, shape: Tuple[int, int]):
+        rows, cols = indices[0], indices[1]
+        self.shape = (int(shape[0]), int(shape[1]))
+        self.nnz = int(rows.numel())
+        self.row_ptr = torch._convert_indices_from_coo_to_csr(rows, self.shape[0], out_int32=True)
+        self.col = cols.to(torch.int32)
+        key = cols * self.shape[0] + rows
+        self.perm = torch.argsort(key, stable=True)
+        self.row_ptr_t = torch._convert_indices_from_coo_to_csr(cols[self.perm], self.shape[1], out_int32=True)
+        self.col_t = rows[self.perm].to(torch.int32)
+
+
+def _spmm_raw(row_ptr, col, vals, x, n_rows):
+    y = torch.empty(n_rows, x.shape[1], dtype=torch.float32, device=x.device)
+    check(lib.topo_spmm_csr(n_rows, ptr(row_ptr, torch.int32), ptr(col, torch.int32), ptr(vals), ptr(x),
+                            x.shape[1], ptr(y), stream()))
+    return y
+
+
+class _SpmmFn(torch.autograd.Function):
+    """y = A x (or A^T x) with gradients to the values (SDDMM on the pattern) and to x."""
+
+    @staticmethod
+    def forward(ctx, vals, x, pattern: CsrPattern, transposed: bool):
+        vals, x = vals.contiguous(), x.contiguous()
+        ctx.save_for_backward(vals, x)
+        ctx.pattern, ctx.transposed = pattern, transposed
+        if transposed:
+            return _spmm_raw(pattern.row_ptr_t, pattern.col_t, vals[pattern.perm].contiguous(), x, pattern.shape[1])
+        return _spmm_raw(pattern.row_ptr, pattern.col, vals, x, pattern.shape[0])
+
+    @staticmethod
+    def backward(ctx, g_y):
+        vals, x = ctx.saved_tensors
+        p, g_y = ctx.pattern, g_y.contiguous()
+        g_vals = torch.empty_like(vals)
+        if ctx.transposed:      # y = A^T x:  dx = A g_y ;  dA[i,j] = x[i] . g_y[j]
+            g_x = _spmm_raw(p.row_ptr, p.col, vals, g_y, p.shape[0])
+            check(lib.topo_sddmm_csr(p.shape[0], ptr(p.row_ptr, torch.int32), ptr(p.col, torch.int32), ptr(x),
+                                     ptr(g_y), x.shape[1], ptr(g_vals), stream()))
+        else:                   # y = A x:    dx = A^T g_y ;  dA[i,j] = g_y[i] . x[j]
+            g_x = _spmm_raw(p.row_ptr_t, p.col_t, vals[p.perm].contiguous(), g_y, p.shape[1])
+            check(lib.topo_sddmm_csr(p.shape[0], ptr(p.row_ptr, torch.int32), ptr(p.col, torch.int32), ptr(g_y),
+                                     ptr(x), x.shape[1], ptr(g_vals), stream()))
+        return g_vals, g_x, None, None
+
+
+# --------------------------------------------------------------------------------------------
+# fused message combine
+# --------------------------------------------------------------------------------------------
+class _CombineFn(torch.autograd.Function):
+    """out = [LayerNorm] sum_k softmax_k(att(m_k)) m_k,  m_k = scale_k (agg_k @ W_k) + x."""
+
+    @staticmethod
+    def forward(ctx, n_msgs, apply_ln, ln_eps, n_rows_dev, x, att_w1, att_b1, att_w2, att_b2, ln_g, ln_b, *rest):
+        aggs = [t.contiguous() for t in rest[:n_msgs]]
+        ws = [t.contiguous() for t in rest[n_msgs:2 * n_msgs]]
+        scales = [t.contiguous() for t in rest[2 * n_msgs:3 * n_msgs]]
+        rows, ch = aggs[0].shape
+        x_c = x.contiguous() if x is not None else None
+        tensors = [att_w1.contiguous(), att_b1.contiguous(), att_w2.contiguous(), att_b2.contiguous(),
+                   ln_g.contiguous(), ln_b.contiguous()]
+        params = _make_params(ch, n_msgs, aggs, ws, scales, x_c, tensors, ln_eps, apply_ln)
+        out = torch.zeros(rows, ch, dtype=torch.float32, device=aggs[0].device)
+        check(lib.topo_sccn_combine_fwd(C.byref(params), rows, ptr(n_rows_dev, torch.int32), ptr(out), stream()))
+        ctx.save_for_backward(x_c, n_rows_dev, *tensors, *aggs, *ws, *scales)
+        ctx.cfg = (n_msgs, bool(apply_ln), float(ln_eps), x is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        n_msgs, apply_ln, ln_eps, has_x = ctx.cfg
+        saved = ctx.saved_tensors
+        x_c, n_rows_dev, tensors = saved[0], saved[1], list(saved[2:8])
+        aggs = list(saved[8:8 + n_msgs])
+        ws = list(saved[8 + n_msgs:8 + 2 * n_msgs])
+        scales = list(saved[8 + 2 * n_msgs:8 + 3 * n_msgs])
+        rows, ch = aggs[0].shape
+        dev = aggs[0].device
+        params = _make_params(ch, n_msgs, aggs, ws, scales, x_c, tensors, ln_eps, apply_ln)
+        g_aggs = [torch.zeros(rows, ch, dtype=torch.float32, device=dev) for _ in range(n_msgs)]
+        g_x = torch.zeros(rows, ch, dtype=torch.float32, device=dev) if has_x else None
+        wprod = [torch.zeros(ch, ch, dtype=torch.float32, device=dev) for _ in range(n_msgs)]
+        g_w1, g_b1 = torch.zeros_like(tensors[0]), torch.zeros_like(tensors[1])
+        g_w2, g_b2 = torch.zeros_like(tensors[2]), torch.zeros_like(tensors[3])
+        g_g, g_b = torch.zeros_like(tensors[4]), torch.zeros_like(tensors[5])
+        grads = CombineGrads()
+        for k in range(3):
+            grads.g_agg[k] = ptr(g_aggs[k]) if k < n_msgs else None
+            grads.g_wprod[k] = ptr(wprod[k]) if k < n_msgs else None
+        grads.g_x = ptr(g_x)
+        grads.g_att_w1, grads.g_att_b1 = ptr(g_w1), ptr(g_b1)
+        grads.g_att_w2, grads.g_att_b2 = ptr(g_w2), ptr(g_b2)
+        grads.g_ln_gamma, grads.g_ln_beta = ptr(g_g), ptr(g_b)
+        workspace = torch.empty(n_msgs * rows * ch, dtype=torch.float32, device=dev)
+        check(lib.topo_sccn_combine_bwd_attention(C.byref(params), rows, ptr(n_rows_dev, torch.int32),
+                                                  ptr(g_out.contiguous()), C.byref(grads), ptr(workspace), stream()))
+        check(lib.topo_sccn_combine_bwd_conv(C.byref(params), rows, ptr(n_rows_dev, torch.int32), C.byref(grads),
+                                             ptr(workspace), stream()))
+        # finish the conv-weight chain: dW_k = scale_k P_k,  dscale_k = <W_k, P_k>
+        g_ws = [wprod[k] * scales[k] for k in range(n_msgs)]
+        g_ss = [(wprod[k] * ws[k]).sum().reshape(scales[k].shape) for k in range(n_msgs)]
+        return (None, None, None, None, g_x, g_w1, g_b1, g_w2, g_b2,
+                g_g if apply_ln else None, g_b if apply_ln else None, *g_aggs, *g_ws, *g_ss)
+
+
+def _make_params(ch, n_msgs, aggs, ws, scales, x, tensors, ln_eps, apply_ln) -> CombineParams:
+    p = CombineParams()
+    p.channels, p.n_msgs = ch, n_msgs
+    for k in range(3):
+        p.agg[k] = ptr(aggs[k]) if k < n_msgs else None
+        p.w[k] = ptr(ws[k]) if k < n_msgs else None
+        p.scale[k] = ptr(scales[k]) if k < n_msgs else None
+    p.x = ptr(x)
+    p.att_w1, p.att_b1, p.att_w2, p.att_b2 = (ptr(t) for t in tensors[:4])
+    p.ln_gamma, p.ln_beta = ptr(tensors[4]), ptr(tensors[5])
+    p.ln_eps, p.apply_ln = float(ln_eps), int(bool(apply_ln))
+    return p
+
+
+# --------------------------------------------------------------------------------------------
+# matrix-free aggregation over a batch of complexes
+# --------------------------------------------------------------------------------------------
+@dataclass
+class BatchedComplex:
+    """A batch of active sub-complexes on the device (the layout of include/topo_b200.h)."""
+    tables: _Tables
+    probs: torch.Tensor       # [B, N] rectified, carries autograd history
+    pos: torch.Tensor         # [B, N] int32
+    act_idx: torch.Tensor     # [B, N] int32
+    counts: torch.Tensor      # [B, 4] int32
+    row_off: torch.Tensor     # [4, B+1] int32
+    rows_max: List[int]       # allocation bound per rank (B * n_r, or exact after a sync)
+    host_counts: Optional[torch.Tensor] = None   # [B, 4] on the host when the caller synchronised
+
+    @property
+    def batch(self) -> int:
+        return int(self.probs.shape[0])
+
+    def view(self, probs: Optional[torch.Tensor] = None) -> ComplexView:
+        v = ComplexView()
+        v.probs = ptr(self.probs.detach() if probs is None else probs)
+        v.pos, v.act_idx = ptr(self.pos, torch.int32), ptr(self.act_idx, torch.int32)
+        v.counts, v.row_off = ptr(self.counts, torch.int32), ptr(self.row_off, torch.int32)
+        v.batch = self.batch
+        return v
+
+    def live_rows(self, rank: int) -> torch.Tensor:
+        """device int32 scalar: total active rows of `rank` in the batch"""
+        return self.row_off[rank, self.batch:self.batch + 1]
+
+
+class _AggregateFn(torch.autograd.Function):
+    """(probs, x0..x3) -> (down0..2, up1..3, same0..3)   [csrc/aggregate.cu]"""
+
+    @staticmethod
+    def forward(ctx, cx: BatchedComplex, probs, x0, x1, x2, x3):
+        xs = [t.contiguous() for t in (x0, x1, x2, x3)]
+        probs = probs.contiguous()
+        ch = xs[0].shape[1]
+        dev = probs.device
+        new = lambda r: torch.zeros(cx.rows_max[r], ch, dtype=torch.float32, device=dev)   # noqa: E731
+        down = [new(0), new(1), new(2), None]
+        up = [None, new(1), new(2), new(3)]
+        same = [new(r) for r in range(4)]
+        view = cx.view(probs)
+        check(lib.topo_sccn_aggregate_fwd(cx.tables.handle, C.byref(view), ch, ptr_array(xs, 4), ptr_array(down, 4),
+                                          ptr_array(up, 4), ptr_array(same, 4), stream()))
+        ctx.save_for_backward(probs, *xs, down[2], up[2], up[3])
+        ctx.cx, ctx.ch = cx, ch
+        return down[0], down[1], down[2], up[1], up[2], up[3], same[0], same[1], same[2], same[3]
+
+    @staticmethod
+    def backward(ctx, gd0, gd1, gd2, gu1, gu2, gu3, gs0, gs1, gs2, gs3):
+        cx, ch = ctx.cx, ctx.ch
+        saved = ctx.saved_tensors
+        probs, xs, down2, up2, up3 = saved[0], list(saved[1:5]), saved[5], saved[6], saved[7]
+        dev = probs.device
+
+        def dense(g, r, clone=False):
+            if g is None:
+                return torch.zeros(cx.rows_max[r], ch, dtype=torch.float32, device=dev)
+            return g.clone() if clone else g.contiguous()
+
+        # g_down[2], g_up[2], g_up[3] are updated in place by the kernel: never hand it autograd's buffers
+        g_down = [dense(gd0, 0), dense(gd1, 1), dense(gd2, 2, clone=True), None]
+        g_up = [None, dense(gu1, 1), dense(gu2, 2, clone=True), dense(gu3, 3, clone=True)]
+        g_same = [dense(g, r) for r, g in enumerate((gs0, gs1, gs2, gs3))]
+        g_x = [torch.zeros(cx.rows_max[r], ch, dtype=torch.float32, device=dev) for r in range(4)]
+        g_probs = torch.zeros_like(probs)
+        view = cx.view(probs)
+        check(lib.topo_sccn_aggregate_bwd(cx.tables.handle, C.byref(view), ch, ptr_array(xs, 4),
+                                          ptr_array([None, None, down2, None], 4), ptr_array([None, None, up2, up3], 4),
+                                          ptr_array(g_down, 4), ptr_array(g_up, 4), ptr_array(g_same, 4),
+                                          ptr_array(g_x, 4), ptr(g_probs), stream()))
+        return (None, g_probs, *g_x)
+
+
+# --------------------------------------------------------------------------------------------
+# modules
+# --------------------------------------------------------------------------------------------
+class Conv(nn.Module):
+    """Stand-in for TopoModelX ``Conv`` as SCCNLayer instantiates it (no bias, no activation)."""
+
+    def __init__(self, in_channels: int, out_channels: int):
+        super().__init__()
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.weight = nn.Parameter(torch.empty(in_channels, out_channels))
+        nn.init.xavier_uniform_(self.weight, gain=1.414)
+
+
+def _present(d, key) -> bool:
+    return d is not None and key in d and d[key] is not None
+
+
+class GradientSCCNLayer(nn.Module):
+    """reference custom_sccn.py:7-138."""
+
+    def __init__(self, channels, max_rank, aggr_func="sum", update_func="relu", residual=True, is_final_layer=False):
+        super().__init__()
+        self.channels, self.max_rank = channels, max_rank
+        self.aggr_func, self.update_func = aggr_func, update_func     # accepted, unused by the forward (as in the reference)
+        self.residual = residual
+        self.is_final_layer = is_final_layer
+        ranks = range(max_rank + 1)
+        self.convs_same_rank = nn.ModuleDict({f"rank_{r}": Conv(channels, channels) for r in ranks})
+        self.convs_low_to_high = nn.ModuleDict({f"rank_{r}": Conv(channels, channels) for r in ranks if r > 0})
+        self.convs_high_to_low = nn.ModuleDict({f"rank_{r}": Conv(channels, channels) for r in ranks if r < max_rank})
+        self.layer_norms = nn.ModuleDict({f"rank_{r}": nn.LayerNorm(channels) for r in ranks})             # :15-18
+        self.message_scales = nn.ParameterDict({k: nn.Parameter(torch.ones(1))                              # :21-25
+                                                for k in ("same_rank", "low_to_high", "high_to_low")})
+        self.message_attention = nn.ModuleDict({                                                            # :28-34
+            f"rank_{r}": nn.Sequential(nn.Linear(channels, channels), nn.GELU(), nn.Linear(channels, 1))
+            for r in ranks})
+
+    # -- shared tail: messages -> output rows --------------------------------------------------
+    def _combine(self, key: str, x: torch.Tensor, msgs: Sequence[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]],
+                 n_rows_dev: Optional[torch.Tensor] = None) -> torch.Tensor:
+        att, ln = self.message_attention[key], self.layer_norms[key]
+        apply_ln = self.training and not self.is_final_layer                                               # :133-134
+        aggs, ws, scales = zip(*msgs)
+        return _CombineFn.apply(len(msgs), apply_ln, ln.eps, n_rows_dev, x if self.residual else None,
+                                att[0].weight, att[0].bias, att[2].weight.reshape(-1), att[2].bias,
+                                ln.weight, ln.bias, *aggs, *ws, *scales)
+
+    # -- reference signature: caller-supplied sparse operators ---------------------------------
+    def forward(self, features, incidences, adjacencies, _patterns: Optional[dict] = None):
+        patterns = {} if _patterns is None else _patterns
+
+        def pattern_of(mat: torch.Tensor):
+            k = id(mat)
+            if k not in patterns:
+                m = mat if mat.is_coalesced() else mat.coalesce()
+                patterns[k] = (CsrPattern(m.indices(), m.shape), m)
+            return patterns[k]
+
+        def aggregate(mat, x_src, transposed):
+            pat, m = pattern_of(mat)
+            return _SpmmFn.apply(m.values(), x_src, pat, transposed)
+
+        out = {}
+        for r in range(self.max_rank + 1):
+            key = f"rank_{r}"
+            if not _present(features, key):                                                                # :69-71
+                out[key] = None
+                continue
+            x = features[key]
+            msgs = []
+            if _present(adjacencies, key):                                                                 # :77-85
+                msgs.append((aggregate(adjacencies[key], x, False),
+                             self.convs_same_rank[key].weight, self.message_scales["same_rank"]))
+            up_key = f"rank_{r + 1}"
+            if r < self.max_rank and _present(features, up_key) and _present(incidences, up_key):         # :88-102
+                msgs.append((aggregate(incidences[up_key], features[up_key], False),
+                             self.convs_high_to_low[key].weight, self.message_scales["high_to_low"]))
+            low_key = f"rank_{r - 1}"
+            if r > 0 and _present(features, low_key) and _present(incidences, key):                       # :105-120
+                msgs.append((aggregate(incidences[key], features[low_key], True),
+                             self.convs_low_to_high[key].weight, self.message_scales["low_to_high"]))
+            if not msgs:                                                                                   # :123-125
+                out[key] = x
+                continue
+            out[key] = self._combine(key, x, msgs) if x.shape[0] else x
+        return out
+
+    # -- batch of complexes, matrix-free --------------------------------------------------------
+    def forward_complex(self, cx: BatchedComplex, xs: Sequence[torch.Tensor]) -> List[torch.Tensor]:
+        if self.max_rank != 3:
+            raise ValueError("forward_complex is built for the reference's max_rank = 3 complexes")
+        d0, d1, d2, u1, u2, u3, s0, s1, s2, s3 = _AggregateFn.apply(cx, cx.probs, *xs)
+        same, down, up = (s0, s1, s2, s3), (d0, d1, d2, None), (None, u1, u2, u3)
+        sc = self.message_scales
+        out = []
+        for r in range(4):
+            key = f"rank_{r}"
+            msgs = [(same[r], self.convs_same_rank[key].weight, sc["same_rank"])]
+            if r < 3:
+                msgs.append((down[r], self.convs_high_to_low[key].weight, sc["high_to_low"]))
+            if r > 0:
+                msgs.append((up[r], self.convs_low_to_high[key].weight, sc["low_to_high"]))
+            out.append(self._combine(key, xs[r], msgs, cx.live_rows(r)) if cx.rows_max[r] else xs[r])
+        return out
+
+
+class GradientSCCN(nn.Module):
+    """reference custom_sccn.py:140-162.  ``residual`` is accepted and ignored (the reference
+    builds every layer with the default residual=True, :147-155); ``update_func`` never reaches
+    the forward."""
+
+    def __init__(self, channels, max_rank, n_layers=2, update_func="sigmoid", residual=False):
+        super().__init__()
+        self.channels, self.max_rank = channels, max_rank
+        self.layers = nn.ModuleList([
+            GradientSCCNLayer(channels=channels, max_rank=max_rank, update_func=update_func,
+                              is_final_layer=(i == n_layers - 1))
+            for i in range(n_layers)])
+
+    def forward(self, features, incidences, adjacencies):
+        patterns: dict = {}          # CSR of each operator is built once and shared by all layers
+        for layer in self.layers:
+            features = layer(features, incidences, adjacencies, _patterns=patterns)
+        return features
+
+    def forward_complex(self, cx: BatchedComplex, xs: Sequence[torch.Tensor]) -> List[torch.Tensor]:
+        for layer in self.layers:
+            xs = layer.forward_complex(cx, xs)
+        return list(xs)
