@@ -87,7 +87,7 @@ def enforce_constraints(v, e, t, tt, tables: OracleTables, eps: float = 1e-10):
 
     def dense_level(own, below, face_matrix, arity):
         log_sum = torch.matmul(face_matrix, torch.log(below + eps))
-        zero = (face_matrix @ (below == 0).float()).bool()
+        zero = (face_matrix @ (below == 0).to(face_matrix.dtype)).bool()
         return _level(own, log_sum, zero, arity)
 
     t_r = dense_level(t, e_r, tables.e2t, 3)

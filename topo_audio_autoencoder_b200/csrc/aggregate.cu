@@ -2,25 +2,30 @@
 //
 // Structured path (whole batch, matrix-free).  The reference applies ten sparse operators per layer
 // (custom_sccn.py:78-81, 95-98, 113-116) that build_sparse_matrices materialised
-// (complex_builder.py:52-70).  Here nothing is materialised: one warp owns one active simplex,
-// walks its static face / coface lists, weights the gathered rows with the rectified probabilities
-// and writes one C-wide row.  Every adjacency factors through the incidences
-// (A1 = I2 I2^T, A2 = I3 I3^T, A3 = I3^T I3, complex_builder.py:62-64), so the same-rank aggregates
-// are incidence gathers of the cross-rank aggregates minus a diagonal term:
+// (complex_builder.py:52-70).  Here nothing is materialised: a group of C/4 lanes owns one active
+// simplex (one float4 per lane, a 128-bit coalesced row), walks its static face / coface lists,
+// weights the gathered rows with the rectified probabilities and writes one C-wide row.
+// Every adjacency factors through the incidences (A1 = I2 I2^T, A2 = I3 I3^T, A3 = I3^T I3,
+// complex_builder.py:62-64), so the same-rank aggregates are incidence gathers of the cross-rank
+// aggregates minus a diagonal term:
 //     down[r] = I_{r+1} X_{r+1}      up[r] = I_r^T X_{r-1}
 //     same[1] = I_2 up[2] - q1 . X1          q1[e] = sum_{t > e} p_t^2
 //     same[2] = I_3 up[3] - q2 . X2          q2[t] = sum_{s > t} p_s^2
 //     same[3] = I_3^T down[2] - c p^2 . X3   c[s]  = number of active faces
 // 88,920 row gathers per sample-layer for the full 20-vertex complex instead of 421,800.
-// All rows are single-owner, so the backward needs no atomics and is deterministic.
+// The gathers are L2-resident (one sample's features are 1.6 MB) and latency bound, so the loops are
+// branch-free (predicated loads) and issue four independent 128-bit row loads per group at a time.
+// All rows are single-owner: the backward needs no atomics and is deterministic.
 //
 // Generic path: CSR SpMM / SDDMM for caller-supplied operators.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace topo {
 namespace {
 
-constexpr int kWarpsPerBlock = 8;
+constexpr int kThreads = 256;
 
 struct Feat {
     const float* p[4];
@@ -34,6 +39,500 @@ struct Sections {
     int chunks[4];  // row chunks per sample for each rank
 };
 
+struct F4 {
+    float v[4];
+    __device__ __forceinline__ void zero() { v[0] = v[1] = v[2] = v[3] = 0.f; }
+    __device__ __forceinline__ void fma(float w, const F4& x) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = fmaf(w, x.v[k], v[k]);
+    }
+    __device__ __forceinline__ void add(const F4& x) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] += x.v[k];
+    }
+    __device__ __forceinline__ float dot(const F4& x) const {
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) s = fmaf(v[k], x.v[k], s);
+        return s;
+    }
+};
+
+// One group's view of its row.  L = lanes per row = C / 4.
+template <int L>
+struct Group {
+    const float* probs;   // this sample's simplex axis
+    const int* pos;
+    int ro[4];            // compact row offset of this sample per rank
+    int lane;             // lane within the group
+    unsigned mask;        // the whole warp takes part in every shuffle
+    bool valid;           // this group owns a live row
+
+    __device__ __forceinline__ F4 load(const float* base, int row) const {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(base) + static_cast<long long>(row) * L + lane);
+        F4 r;
+        r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w;
+        return r;
+    }
+    __device__ __forceinline__ F4 load_if(bool ok, const float* base, int row) const {
+        F4 r;
+        r.zero();
+        if (ok) r = load(base, row);
+        return r;
+    }
+    __device__ __forceinline__ F4 load_rw(const float* base, int row) const {   // not through the read-only path
+        const float4 t = *(reinterpret_cast<const float4*>(base) + static_cast<long long>(row) * L + lane);
+        F4 r;
+        r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w;
+        return r;
+    }
+    __device__ __forceinline__ void store(float* base, int row, const F4& x) const {
+        if (valid)
+            *(reinterpret_cast<float4*>(base) + static_cast<long long>(row) * L + lane) = make_float4(x.v[0], x.v[1], x.v[2], x.v[3]);
+    }
+    __device__ __forceinline__ void accumulate(float* base, int row, const F4& x) const {
+        if (valid) {
+            float4* p = reinterpret_cast<float4*>(base) + static_cast<long long>(row) * L + lane;
+            float4 t = *p;
+            t.x += x.v[0]; t.y += x.v[1]; t.z += x.v[2]; t.w += x.v[3];
+            *p = t;
+        }
+    }
+    __device__ __forceinline__ float group_sum(float v) const {
+#pragma unroll
+        for (int o = L / 2; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o, L);
+        return v;
+    }
+    __device__ __forceinline__ int row_of(const DeviceTables& d, int r, int id) const {
+        const int p = pos[d.off[r] + id];
+        return p < 0 ? -1 : ro[r] + p;
+    }
+};
+
+// f(ok, row, p_s) for every coface slot of simplex `id` (rank R), four slots at a time; ok == false
+// marks an inactive coface or a padding slot (its load is predicated off).
+template <int L, int R, typename F>
+__device__ __forceinline__ void for_cofaces(const DeviceTables& d, const Group<L>& g, int id, F&& f) {
+    const int w = d.ncof[R];
+    const int* cof = d.cofaces[R] + static_cast<long long>(id) * w;
+    for (int jb = 0; jb < w; jb += L) {
+        const int j = jb + g.lane;
+        int row = -1;
+        float ps = 0.f;
+        if (j < w) {
+            const int s = __ldg(cof + j);
+            ps = g.probs[d.off[R + 1] + s];
+            row = (ps != 0.0f) ? g.row_of(d, R + 1, s) : -1;
+        }
+        const int m = min(L, w - jb);
+        for (int j4 = 0; j4 < m; j4 += 4) {
+            int rr[4];
+            float pp[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                rr[q] = __shfl_sync(g.mask, row, (j4 + q) & (L - 1), L);
+                pp[q] = __shfl_sync(g.mask, ps, (j4 + q) & (L - 1), L);
+                if (j4 + q >= m) rr[q] = -1;
+            }
+            f(rr, pp);
+        }
+    }
+}
+
+// rows of the (R+1) faces of simplex `id` (rank R >= 1); -1 for an inactive face
+template <int L, int R>
+__device__ __forceinline__ void face_rows(const DeviceTables& d, const Group<L>& g, int id, int (&rows)[R + 1]) {
+    const int* fc = d.faces[R] + static_cast<long long>(id) * (R + 1);
+#pragma unroll
+    for (int a = 0; a <= R; ++a) rows[a] = g.row_of(d, R - 1, __ldg(fc + a));
+}
+
+template <int L>
+__device__ __forceinline__ void gather4(const Group<L>& g, const float* base, const int (&rr)[4], F4 (&v)[4]) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) v[q] = g.load_if(rr[q] >= 0, base, rr[q]);
+}
+
+// Decode blockIdx.x -> (rank, sample, local row) for this group.  Groups past the live rows stay in the
+// kernel (the shuffles are warp-wide) with valid == false and id == 0.
+template <int L>
+__device__ __forceinline__ void locate(const DeviceTables& d, const Sections& sec, const topo_complex_view& cv,
+                                       Group<L>* g, int* rank, int* row, int* id, long long* axis) {
+    constexpr int kGroups = kThreads / L;
+    const int blk = blockIdx.x;
+    const int r = (blk >= sec.begin[1]) + (blk >= sec.begin[2]) + (blk >= sec.begin[3]);
+    // selects instead of sec.begin[r]: a runtime index would copy the parameter struct to local memory
+    const int begin = r == 0 ? sec.begin[0] : (r == 1 ? sec.begin[1] : (r == 2 ? sec.begin[2] : sec.begin[3]));
+    const int chunks = r == 0 ? sec.chunks[0] : (r == 1 ? sec.chunks[1] : (r == 2 ? sec.chunks[2] : sec.chunks[3]));
+    const int off_r = r == 0 ? d.off[0] : (r == 1 ? d.off[1] : (r == 2 ? d.off[2] : d.off[3]));
+    const int rel = blk - begin;
+    const int b = rel / chunks;
+    const int i = (rel - b * chunks) * kGroups + threadIdx.x / L;
+    const long long ax = static_cast<long long>(b) * d.off[4];
+    g->probs = cv.probs + ax;
+    g->pos = cv.pos + ax;
+    g->lane = threadIdx.x % L;
+    g->mask = 0xffffffffu;
+    g->valid = i < cv.counts[b * 4 + r];
+    const int B1 = static_cast<int>(cv.batch) + 1;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) g->ro[q] = cv.row_off[q * B1 + b];
+    const int ro_r = r == 0 ? g->ro[0] : (r == 1 ? g->ro[1] : (r == 2 ? g->ro[2] : g->ro[3]));
+    *rank = r;
+    *row = ro_r + (g->valid ? i : 0);
+    *id = g->valid ? cv.act_idx[ax + off_r + i] : 0;
+    *axis = ax;
+}
+
+// ------------------------------------------------------------------ forward, phase 1: cross-rank
+template <int L, int R>
+__device__ __forceinline__ void cross_fwd_body(const DeviceTables& d, const Group<L>& g, int row, int id, const Feat& x,
+                                               const FeatMut& down, const FeatMut& up) {
+    if constexpr (R < 3) {             // down[R] = sum over cofaces p_s X_{R+1}[s]
+        if (d.cnt[R + 1] > 0) {
+            F4 acc;
+            acc.zero();
+            for_cofaces<L, R>(d, g, id, [&](const int (&rr)[4], const float (&pp)[4]) {
+                F4 v[4];
+                gather4(g, x.p[R + 1], rr, v);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) acc.fma(pp[q], v[q]);
+            });
+            g.store(down.p[R], row, acc);
+        }
+    }
+    if constexpr (R > 0) {             // up[R] = p_id * sum over active faces X_{R-1}[f]
+        int fr[R + 1];
+        face_rows<L, R>(d, g, id, fr);
+        F4 acc;
+        acc.zero();
+        F4 v[R + 1];
+#pragma unroll
+        for (int a = 0; a <= R; ++a) v[a] = g.load_if(fr[a] >= 0, x.p[R - 1], fr[a]);
+#pragma unroll
+        for (int a = 0; a <= R; ++a) acc.add(v[a]);
+        const float p = g.probs[d.off[R] + id];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc.v[k] *= p;
+        g.store(up.p[R], row, acc);
+    }
+}
+
+template <int L>
+__global__ void __launch_bounds__(kThreads) agg_cross_fwd(const DeviceTables d, const Sections sec,
+                                                          const topo_complex_view cv, const Feat x, const FeatMut down,
+                                                          const FeatMut up) {
+    Group<L> g;
+    int r, row, id;
+    long long axis;
+    locate<L>(d, sec, cv, &g, &r, &row, &id, &axis);
+    switch (r) {
+        case 0: cross_fwd_body<L, 0>(d, g, row, id, x, down, up); break;
+        case 1: cross_fwd_body<L, 1>(d, g, row, id, x, down, up); break;
+        case 2: cross_fwd_body<L, 2>(d, g, row, id, x, down, up); break;
+        default: cross_fwd_body<L, 3>(d, g, row, id, x, down, up); break;
+    }
+}
+
+// ------------------------------------------------------------------ forward, phase 2: same-rank
+// A0[v,v'] = p_e: walk the vertex's edges, gather the other endpoint.  f(rows[4], p_e[4]).
+template <int L, typename F>
+__device__ __forceinline__ void for_vertex_neighbours(const DeviceTables& d, const Group<L>& g, int id, F&& f) {
+    const int w = d.ncof[0];
+    const int* cof = d.cofaces[0] + static_cast<long long>(id) * w;
+    for (int jb = 0; jb < w; jb += L) {
+        const int j = jb + g.lane;
+        int orow = -1;
+        float pe = 0.f;
+        if (j < w) {
+            const int e = __ldg(cof + j);
+            pe = g.probs[d.off[1] + e];
+            const int2 ends = __ldg(reinterpret_cast<const int2*>(d.faces[1]) + e);
+            orow = (pe != 0.0f) ? g.row_of(d, 0, ends.x == id ? ends.y : ends.x) : -1;
+        }
+        const int m = min(L, w - jb);
+        for (int j4 = 0; j4 < m; j4 += 4) {
+            int rr[4];
+            float pp[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                rr[q] = __shfl_sync(g.mask, orow, (j4 + q) & (L - 1), L);
+                pp[q] = __shfl_sync(g.mask, pe, (j4 + q) & (L - 1), L);
+                if (j4 + q >= m) rr[q] = -1;
+            }
+            f(rr, pp);
+        }
+    }
+}
+
+template <int L, int R>
+__device__ __forceinline__ void same_fwd_body(const DeviceTables& d, const Group<L>& g, int row, int id, const Feat& x,
+                                              const Feat& down, const Feat& up, const FeatMut& same) {
+    F4 acc;
+    acc.zero();
+    if constexpr (R == 0) {
+        for_vertex_neighbours<L>(d, g, id, [&](const int (&rr)[4], const float (&pp)[4]) {
+            F4 v[4];
+            gather4(g, x.p[0], rr, v);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc.fma(pp[q], v[q]);
+        });
+    } else if constexpr (R < 3) {
+        // same[R] = sum_{s > id} p_s up[R+1][s]  -  (sum p_s^2) X_R[id]
+        float qsum = 0.f;
+        if (d.cnt[R + 1] > 0)
+            for_cofaces<L, R>(d, g, id, [&](const int (&rr)[4], const float (&pp)[4]) {
+                F4 v[4];
+                gather4(g, up.p[R + 1], rr, v);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    acc.fma(pp[q], v[q]);
+                    if (rr[q] >= 0) qsum = fmaf(pp[q], pp[q], qsum);
+                }
+            });
+        const F4 own = g.load_if(g.valid, x.p[R], row);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc.v[k] = fmaf(-qsum, own.v[k], acc.v[k]);
+    } else {
+        // same[3] = p (sum_{t < id, active} down[2][t] - c p X_3[id])
+        int fr[4];
+        face_rows<L, 3>(d, g, id, fr);
+        F4 v[4];
+        gather4(g, down.p[2], fr, v);
+        int n_faces = 0;
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            acc.add(v[a]);
+            n_faces += fr[a] >= 0;
+        }
+        const float p = g.probs[d.off[3] + id];
+        const F4 own = g.load_if(g.valid, x.p[3], row);
+        const float cp = static_cast<float>(n_faces) * p;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc.v[k] = p * fmaf(-cp, own.v[k], acc.v[k]);
+    }
+    g.store(same.p[R], row, acc);
+}
+
+template <int L>
+__global__ void __launch_bounds__(kThreads) agg_same_fwd(const DeviceTables d, const Sections sec,
+                                                         const topo_complex_view cv, const Feat x, const Feat down,
+                                                         const Feat up, const FeatMut same) {
+    Group<L> g;
+    int r, row, id;
+    long long axis;
+    locate<L>(d, sec, cv, &g, &r, &row, &id, &axis);
+    switch (r) {
+        case 0: same_fwd_body<L, 0>(d, g, row, id, x, down, up, same); break;
+        case 1: same_fwd_body<L, 1>(d, g, row, id, x, down, up, same); break;
+        case 2: same_fwd_body<L, 2>(d, g, row, id, x, down, up, same); break;
+        default: same_fwd_body<L, 3>(d, g, row, id, x, down, up, same); break;
+    }
+}
+
+// ------------------------------------------------------------------ backward, stage X: same-rank
+// Updates g_up[2], g_up[3], g_down[2] in place (owner rows only), adds the diagonal and A0 terms to
+// g_x, and the direct probability derivatives to g_probs.
+template <int L, int R>
+__device__ __forceinline__ void same_bwd_body(const DeviceTables& d, const Group<L>& g, int row, int id, long long axis,
+                                              const Feat& x, const Feat& down, const Feat& up, const Feat& g_same,
+                                              const FeatMut& g_down, const FeatMut& g_up, const FeatMut& g_x,
+                                              float* __restrict__ g_probs) {
+    const float p = g.probs[d.off[R] + id];
+    float gp = 0.f;            // d loss / d p_id collected by this group (lane-partial dot products)
+    F4 gx;                     // addition to g_x[R][row]
+    gx.zero();
+
+    if constexpr (R == 0) {
+        // same[0] = A0 X0, A0 symmetric:  g_x0[v] += sum_{v'} p_e g_same0[v']
+        for_vertex_neighbours<L>(d, g, id, [&](const int (&rr)[4], const float (&pp)[4]) {
+            F4 v[4];
+            gather4(g, g_same.p[0], rr, v);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) gx.fma(pp[q], v[q]);
+        });
+    }
+    if constexpr (R == 1) {
+        // owner of p_e for A0: d/dp_e = <g_same0[v], X0[v']> + <g_same0[v'], X0[v]>
+        int fr[2];
+        face_rows<L, 1>(d, g, id, fr);
+        const bool both = fr[0] >= 0 && fr[1] >= 0;
+        const F4 ga = g.load_if(both, g_same.p[0], fr[0]), gb = g.load_if(both, g_same.p[0], fr[1]);
+        const F4 xa = g.load_if(both, x.p[0], fr[0]), xb = g.load_if(both, x.p[0], fr[1]);
+        gp += ga.dot(xb) + gb.dot(xa);
+    }
+    if constexpr (R == 1 || R == 2) {
+        // diagonal of same[R]: g_x[R] -= q g_same[R],  q = sum_{s > id} p_s^2
+        if (d.cnt[R + 1] > 0) {
+            float qsum = 0.f;
+            for_cofaces<L, R>(d, g, id, [&](const int (&rr)[4], const float (&pp)[4]) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (rr[q] >= 0) qsum = fmaf(pp[q], pp[q], qsum);
+            });
+            const F4 gs = g.load_if(g.valid, g_same.p[R], row);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) gx.v[k] = fmaf(-qsum, gs.v[k], gx.v[k]);
+        }
+    }
+    if constexpr (R == 2 || R == 3) {
+        // owner of p_id for same[R-1] = I_R up[R] - q X_{R-1}:
+        //   Rsum = sum_{f < id} g_same[R-1][f];  g_up[R][id] += p Rsum;
+        //   d/dp = <Rsum, up[R][id]> - 2 p sum_f <g_same[R-1][f], X_{R-1}[f]>
+        int fr[R + 1];
+        face_rows<L, R>(d, g, id, fr);
+        F4 gf[R + 1], xf[R + 1];
+#pragma unroll
+        for (int a = 0; a <= R; ++a) {
+            gf[a] = g.load_if(fr[a] >= 0, g_same.p[R - 1], fr[a]);
+            xf[a] = g.load_if(fr[a] >= 0, x.p[R - 1], fr[a]);
+        }
+        F4 rsum;
+        rsum.zero();
+        float diag = 0.f;
+#pragma unroll
+        for (int a = 0; a <= R; ++a) {
+            rsum.add(gf[a]);
+            diag += gf[a].dot(xf[a]);
+        }
+        const F4 u = g.load_if(g.valid, up.p[R], row);
+        gp += rsum.dot(u) - 2.0f * p * diag;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) rsum.v[k] *= p;
+        g.accumulate(g_up.p[R], row, rsum);
+    }
+    if constexpr (R == 2) {
+        if (d.cnt[3] > 0) {
+            // same[3] = I_3^T down[2] - ...:  g_down[2][t] += sum_{s > t} p_s g_same[3][s]
+            F4 acc;
+            acc.zero();
+            for_cofaces<L, 2>(d, g, id, [&](const int (&rr)[4], const float (&pp)[4]) {
+                F4 v[4];
+                gather4(g, g_same.p[3], rr, v);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) acc.fma(pp[q], v[q]);
+            });
+            g.accumulate(g_down.p[2], row, acc);
+        }
+    }
+    if constexpr (R == 3) {
+        // direct p dependence of same[3] = p sum_t down[2][t] - c p^2 X3, and its diagonal
+        int fr[4];
+        face_rows<L, 3>(d, g, id, fr);
+        F4 v[4];
+        gather4(g, down.p[2], fr, v);
+        F4 sum_d;
+        sum_d.zero();
+        int n_faces = 0;
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            sum_d.add(v[a]);
+            n_faces += fr[a] >= 0;
+        }
+        const F4 gs = g.load_if(g.valid, g_same.p[3], row);
+        const F4 own = g.load_if(g.valid, x.p[3], row);
+        const float cf = static_cast<float>(n_faces);
+        gp += gs.dot(sum_d) - 2.0f * cf * p * gs.dot(own);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) gx.v[k] = fmaf(-cf * p * p, gs.v[k], gx.v[k]);
+    }
+
+    g.accumulate(g_x.p[R], row, gx);
+    if constexpr (R >= 1) {
+        gp = g.group_sum(gp);
+        if (g.lane == 0 && g.valid) g_probs[axis + d.off[R] + id] += gp;
+    }
+}
+
+template <int L>
+__global__ void __launch_bounds__(kThreads) agg_same_bwd(const DeviceTables d, const Sections sec,
+                                                         const topo_complex_view cv, const Feat x, const Feat down,
+                                                         const Feat up, const Feat g_same, const FeatMut g_down,
+                                                         const FeatMut g_up, const FeatMut g_x, float* __restrict__ g_probs) {
+    Group<L> g;
+    int r, row, id;
+    long long axis;
+    locate<L>(d, sec, cv, &g, &r, &row, &id, &axis);
+    switch (r) {
+        case 0: same_bwd_body<L, 0>(d, g, row, id, axis, x, down, up, g_same, g_down, g_up, g_x, g_probs); break;
+        case 1: same_bwd_body<L, 1>(d, g, row, id, axis, x, down, up, g_same, g_down, g_up, g_x, g_probs); break;
+        case 2: same_bwd_body<L, 2>(d, g, row, id, axis, x, down, up, g_same, g_down, g_up, g_x, g_probs); break;
+        default: same_bwd_body<L, 3>(d, g, row, id, axis, x, down, up, g_same, g_down, g_up, g_x, g_probs); break;
+    }
+}
+
+// ------------------------------------------------------------------ backward, stage Y: cross-rank
+// With the TOTAL g_down / g_up:  down[R-1] = I_R X_R,  up[R] = I_R^T X_{R-1}.
+template <int L, int R>
+__device__ __forceinline__ void cross_bwd_body(const DeviceTables& d, const Group<L>& g, int row, int id, long long axis,
+                                               const Feat& x, const Feat& g_down, const Feat& g_up, const FeatMut& g_x,
+                                               float* __restrict__ g_probs) {
+    F4 gx;
+    gx.zero();
+    float gp = 0.f;
+    if constexpr (R >= 1) {
+        const float p = g.probs[d.off[R] + id];
+        // as the coface s of down[R-1]:  Rsum = sum_f g_down[R-1][f];  g_x += p Rsum;  d/dp = <Rsum, X_R[s]>
+        // as the target of up[R]:        d/dp = <g_up[R][s], sum_f X_{R-1}[f]>
+        int fr[R + 1];
+        face_rows<L, R>(d, g, id, fr);
+        F4 gf[R + 1], xf[R + 1];
+#pragma unroll
+        for (int a = 0; a <= R; ++a) {
+            gf[a] = g.load_if(fr[a] >= 0, g_down.p[R - 1], fr[a]);
+            xf[a] = g.load_if(fr[a] >= 0, x.p[R - 1], fr[a]);
+        }
+        F4 rsum, qsum;
+        rsum.zero();
+        qsum.zero();
+#pragma unroll
+        for (int a = 0; a <= R; ++a) {
+            rsum.add(gf[a]);
+            qsum.add(xf[a]);
+        }
+        const F4 own = g.load_if(g.valid, x.p[R], row);
+        const F4 gu = g.load_if(g.valid, g_up.p[R], row);
+        gp = rsum.dot(own) + qsum.dot(gu);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) gx.v[k] = p * rsum.v[k];
+    }
+    if constexpr (R < 3) {
+        if (d.cnt[R + 1] > 0) {
+            // as a face of up[R+1]:  g_x[R][f] += sum_{s > f} p_s g_up[R+1][s]
+            for_cofaces<L, R>(d, g, id, [&](const int (&rr)[4], const float (&pp)[4]) {
+                F4 v[4];
+                gather4(g, g_up.p[R + 1], rr, v);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) gx.fma(pp[q], v[q]);
+            });
+        }
+    }
+    g.accumulate(g_x.p[R], row, gx);
+    if constexpr (R >= 1) {
+        gp = g.group_sum(gp);
+        if (g.lane == 0 && g.valid) g_probs[axis + d.off[R] + id] += gp;
+    }
+}
+
+template <int L>
+__global__ void __launch_bounds__(kThreads) agg_cross_bwd(const DeviceTables d, const Sections sec,
+                                                          const topo_complex_view cv, const Feat x, const Feat g_down,
+                                                          const Feat g_up, const FeatMut g_x, float* __restrict__ g_probs) {
+    Group<L> g;
+    int r, row, id;
+    long long axis;
+    locate<L>(d, sec, cv, &g, &r, &row, &id, &axis);
+    switch (r) {
+        case 0: cross_bwd_body<L, 0>(d, g, row, id, axis, x, g_down, g_up, g_x, g_probs); break;
+        case 1: cross_bwd_body<L, 1>(d, g, row, id, axis, x, g_down, g_up, g_x, g_probs); break;
+        case 2: cross_bwd_body<L, 2>(d, g, row, id, axis, x, g_down, g_up, g_x, g_probs); break;
+        default: cross_bwd_body<L, 3>(d, g, row, id, axis, x, g_down, g_up, g_x, g_probs); break;
+    }
+}
+
+// ------------------------------------------------------------------ generic CSR
+constexpr int kWarpsPerBlock = 8;
+
 template <int VEC>
 struct Acc {
     float v[VEC];
@@ -45,365 +544,15 @@ struct Acc {
 #pragma unroll
         for (int k = 0; k < VEC; ++k) v[k] = fmaf(w, x.v[k], v[k]);
     }
-    __device__ __forceinline__ void add(const Vec<VEC>& x) {
-#pragma unroll
-        for (int k = 0; k < VEC; ++k) v[k] += x.v[k];
-    }
-    __device__ __forceinline__ float dot(const Vec<VEC>& x) const {
-        float s = 0.f;
-#pragma unroll
-        for (int k = 0; k < VEC; ++k) s = fmaf(v[k], x.v[k], s);
-        return s;
-    }
 };
 
 template <int VEC>
-__device__ __forceinline__ Vec<VEC> load_row(const float* base, int row, int lane) {
+__device__ __forceinline__ Vec<VEC> load_row(const float* base, long long row, int lane) {
     Vec<VEC> x;
-    x.load(base + (static_cast<long long>(row) * 32 + lane) * VEC);
+    x.load(base + (row * 32 + lane) * VEC);
     return x;
 }
-// plain (non read-only-path) load for arrays another launch phase of the same kernel may write
-template <int VEC>
-__device__ __forceinline__ Vec<VEC> load_row_rw(const float* base, int row, int lane) {
-    Vec<VEC> x;
-    const float* p = base + (static_cast<long long>(row) * 32 + lane) * VEC;
-#pragma unroll
-    for (int k = 0; k < VEC; ++k) x.v[k] = p[k];
-    return x;
-}
-template <int VEC>
-__device__ __forceinline__ void store_row(float* base, int row, int lane, const float (&v)[VEC]) {
-    Vec<VEC> x;
-#pragma unroll
-    for (int k = 0; k < VEC; ++k) x.v[k] = v[k];
-    x.store(base + (static_cast<long long>(row) * 32 + lane) * VEC);
-}
-template <int VEC>
-__device__ __forceinline__ void add_row(float* base, int row, int lane, const float (&v)[VEC]) {
-    float* p = base + (static_cast<long long>(row) * 32 + lane) * VEC;
-    Vec<VEC> x;
-#pragma unroll
-    for (int k = 0; k < VEC; ++k) x.v[k] = p[k] + v[k];
-    x.store(p);
-}
 
-// One warp's view of its sample.
-struct WarpCtx {
-    const DeviceTables* d;
-    const float* probs;   // this sample's simplex axis
-    const int* pos;
-    int ro[4];            // compact row offset of this sample per rank
-    int lane;
-
-    __device__ __forceinline__ int row_of(int r, int id) const {
-        const int p = pos[d->off[r] + id];
-        return p < 0 ? -1 : ro[r] + p;
-    }
-    __device__ __forceinline__ float prob(int r, int id) const { return probs[d->off[r] + id]; }
-};
-
-// f(row, p_s) for every active coface s (p_s != 0) of simplex `id` of rank r, ascending.
-template <typename F>
-__device__ __forceinline__ void for_cofaces(const WarpCtx& c, int r, int id, F&& f) {
-    const int w = c.d->ncof[r];
-    const int* cof = c.d->cofaces[r] + static_cast<long long>(id) * w;
-    for (int jb = 0; jb < w; jb += 32) {
-        const int j = jb + c.lane;
-        int row = -1;
-        float ps = 0.f;
-        if (j < w) {
-            const int s = __ldg(cof + j);
-            ps = c.prob(r + 1, s);
-            row = (ps != 0.0f) ? c.row_of(r + 1, s) : -1;
-        }
-        const int m = min(32, w - jb);
-#pragma unroll 4
-        for (int jj = 0; jj < m; ++jj) {
-            const int rr = __shfl_sync(0xffffffffu, row, jj);
-            const float pp = __shfl_sync(0xffffffffu, ps, jj);
-            if (rr >= 0) f(rr, pp);
-        }
-    }
-}
-
-// f(row) for every active face of simplex `id` of rank r >= 1, ascending.  Returns the count.
-template <typename F>
-__device__ __forceinline__ int for_faces(const WarpCtx& c, int r, int id, F&& f) {
-    const int* fc = c.d->faces[r] + static_cast<long long>(id) * (r + 1);
-    int n = 0;
-    for (int a = 0; a <= r; ++a) {
-        const int row = c.row_of(r - 1, __ldg(fc + a));
-        if (row >= 0) { f(row); ++n; }
-    }
-    return n;
-}
-
-// Decode blockIdx.x -> (rank, sample, first local row); returns false when this warp has no row.
-__device__ __forceinline__ bool locate(const DeviceTables& d, const Sections& sec, const topo_complex_view& cv,
-                                       WarpCtx* c, int* rank, int* local, int* id) {
-    const int blk = blockIdx.x;
-    const int r = (blk >= sec.begin[1]) + (blk >= sec.begin[2]) + (blk >= sec.begin[3]);
-    const int rel = blk - sec.begin[r];
-    const int b = rel / sec.chunks[r];
-    const int i = (rel % sec.chunks[r]) * kWarpsPerBlock + (threadIdx.x >> 5);
-    if (i >= cv.counts[b * 4 + r]) return false;
-    const long long axis = static_cast<long long>(b) * d.off[4];
-    c->d = &d;
-    c->probs = cv.probs + axis;
-    c->pos = cv.pos + axis;
-    c->lane = threadIdx.x & 31;
-    const int B1 = static_cast<int>(cv.batch) + 1;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) c->ro[q] = cv.row_off[q * B1 + b];
-    *rank = r;
-    *local = i;
-    *id = cv.act_idx[axis + d.off[r] + i];
-    return true;
-}
-
-// ------------------------------------------------------------------ forward, phase 1: cross-rank
-template <int VEC>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32) agg_cross_fwd(DeviceTables d, Sections sec,
-                                                                     topo_complex_view cv, Feat x, FeatMut down,
-                                                                     FeatMut up) {
-    WarpCtx c;
-    int r, i, id;
-    if (!locate(d, sec, cv, &c, &r, &i, &id)) return;
-    const int row = c.ro[r] + i;
-    if (r < 3 && d.cnt[r + 1] > 0) {   // down[r] = sum over cofaces p_s X_{r+1}[s]
-        Acc<VEC> acc;
-        acc.zero();
-        for_cofaces(c, r, id, [&](int rr, float ps) { acc.fma(ps, load_row<VEC>(x.p[r + 1], rr, c.lane)); });
-        store_row<VEC>(down.p[r], row, c.lane, acc.v);
-    }
-    if (r > 0) {                       // up[r] = p_id * sum over active faces X_{r-1}[f]
-        Acc<VEC> acc;
-        acc.zero();
-        for_faces(c, r, id, [&](int rr) { acc.add(load_row<VEC>(x.p[r - 1], rr, c.lane)); });
-        const float p = c.prob(r, id);
-#pragma unroll
-        for (int k = 0; k < VEC; ++k) acc.v[k] *= p;
-        store_row<VEC>(up.p[r], row, c.lane, acc.v);
-    }
-}
-
-// ------------------------------------------------------------------ forward, phase 2: same-rank
-template <int VEC>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32) agg_same_fwd(DeviceTables d, Sections sec,
-                                                                    topo_complex_view cv, Feat x, Feat down, Feat up,
-                                                                    FeatMut same) {
-    WarpCtx c;
-    int r, i, id;
-    if (!locate(d, sec, cv, &c, &r, &i, &id)) return;
-    const int row = c.ro[r] + i;
-    Acc<VEC> acc;
-    acc.zero();
-    if (r == 0) {
-        // A0[v,v'] = p_e: walk the vertex's edges, gather the other endpoint
-        const int w = d.ncof[0];
-        const int* cof = d.cofaces[0] + static_cast<long long>(id) * w;
-        for (int jb = 0; jb < w; jb += 32) {
-            const int j = jb + c.lane;
-            int orow = -1;
-            float pe = 0.f;
-            if (j < w) {
-                const int e = __ldg(cof + j);
-                pe = c.prob(1, e);
-                const int2 ends = __ldg(reinterpret_cast<const int2*>(d.faces[1]) + e);
-                orow = (pe != 0.0f) ? c.row_of(0, ends.x == id ? ends.y : ends.x) : -1;
-            }
-            const int m = min(32, w - jb);
-#pragma unroll 4
-            for (int jj = 0; jj < m; ++jj) {
-                const int rr = __shfl_sync(0xffffffffu, orow, jj);
-                const float pp = __shfl_sync(0xffffffffu, pe, jj);
-                if (rr >= 0) acc.fma(pp, load_row<VEC>(x.p[0], rr, c.lane));
-            }
-        }
-    } else if (r < 3) {
-        // same[r] = sum_{s > id} p_s up[r+1][s]  -  (sum p_s^2) X_r[id]
-        float q = 0.f;
-        if (d.cnt[r + 1] > 0)
-            for_cofaces(c, r, id, [&](int rr, float ps) {
-                acc.fma(ps, load_row<VEC>(up.p[r + 1], rr, c.lane));
-                q = fmaf(ps, ps, q);
-            });
-        const Vec<VEC> own = load_row<VEC>(x.p[r], row, c.lane);
-#pragma unroll
-        for (int k = 0; k < VEC; ++k) acc.v[k] = fmaf(-q, own.v[k], acc.v[k]);
-    } else {
-        // same[3] = p (sum_{t < id, active} down[2][t] - c p X_3[id])
-        const int n_faces = for_faces(c, 3, id, [&](int rr) { acc.add(load_row<VEC>(down.p[2], rr, c.lane)); });
-        const float p = c.prob(3, id);
-        const Vec<VEC> own = load_row<VEC>(x.p[3], row, c.lane);
-        const float cp = static_cast<float>(n_faces) * p;
-#pragma unroll
-        for (int k = 0; k < VEC; ++k) acc.v[k] = p * fmaf(-cp, own.v[k], acc.v[k]);
-    }
-    store_row<VEC>(same.p[r], row, c.lane, acc.v);
-}
-
-// ------------------------------------------------------------------ backward, stage X: same-rank
-// Updates g_up[2], g_up[3], g_down[2] in place (owner rows only), adds the diagonal and A0 terms to
-// g_x, and the direct probability derivatives to g_probs.
-template <int VEC>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32) agg_same_bwd(DeviceTables d, Sections sec,
-                                                                    topo_complex_view cv, Feat x, Feat down, Feat up,
-                                                                    Feat g_same, FeatMut g_down, FeatMut g_up,
-                                                                    FeatMut g_x, float* __restrict__ g_probs) {
-    WarpCtx c;
-    int r, i, id;
-    if (!locate(d, sec, cv, &c, &r, &i, &id)) return;
-    const int row = c.ro[r] + i;
-    const long long axis = c.probs - cv.probs;
-    const float p = c.prob(r, id);
-    float gp = 0.f;            // d loss / d p_id collected by this warp (lane-partial dot products)
-    Acc<VEC> gx;               // addition to g_x[r][row]
-    gx.zero();
-
-    if (r == 0) {
-        // same[0] = A0 X0, A0 symmetric:  g_x0[v] += sum_{v'} p_e g_same0[v']
-        const int w = d.ncof[0];
-        const int* cof = d.cofaces[0] + static_cast<long long>(id) * w;
-        for (int jb = 0; jb < w; jb += 32) {
-            const int j = jb + c.lane;
-            int orow = -1;
-            float pe = 0.f;
-            if (j < w) {
-                const int e = __ldg(cof + j);
-                pe = c.prob(1, e);
-                const int2 ends = __ldg(reinterpret_cast<const int2*>(d.faces[1]) + e);
-                orow = (pe != 0.0f) ? c.row_of(0, ends.x == id ? ends.y : ends.x) : -1;
-            }
-            const int m = min(32, w - jb);
-#pragma unroll 4
-            for (int jj = 0; jj < m; ++jj) {
-                const int rr = __shfl_sync(0xffffffffu, orow, jj);
-                const float pp = __shfl_sync(0xffffffffu, pe, jj);
-                if (rr >= 0) gx.fma(pp, load_row<VEC>(g_same.p[0], rr, c.lane));
-            }
-        }
-    }
-    if (r == 1) {
-        // owner of p_e for A0: d/dp_e = <g_same0[v], X0[v']> + <g_same0[v'], X0[v]>
-        const int2 ends = __ldg(reinterpret_cast<const int2*>(d.faces[1]) + id);
-        const int ra = c.row_of(0, ends.x), rb = c.row_of(0, ends.y);
-        if (ra >= 0 && rb >= 0) {
-            const Vec<VEC> ga = load_row<VEC>(g_same.p[0], ra, c.lane), gb = load_row<VEC>(g_same.p[0], rb, c.lane);
-            const Vec<VEC> xa = load_row<VEC>(x.p[0], ra, c.lane), xb = load_row<VEC>(x.p[0], rb, c.lane);
-#pragma unroll
-            for (int k = 0; k < VEC; ++k) gp += ga.v[k] * xb.v[k] + gb.v[k] * xa.v[k];
-        }
-    }
-    if (r == 1 || r == 2) {
-        // diagonal of same[r]: g_x[r] -= q g_same[r],  q = sum_{s > id} p_s^2
-        if (d.cnt[r + 1] > 0) {
-            float q = 0.f;
-            for_cofaces(c, r, id, [&](int, float ps) { q = fmaf(ps, ps, q); });
-            const Vec<VEC> g = load_row<VEC>(g_same.p[r], row, c.lane);
-#pragma unroll
-            for (int k = 0; k < VEC; ++k) gx.v[k] = fmaf(-q, g.v[k], gx.v[k]);
-        }
-    }
-    if (r == 2 || r == 3) {
-        // owner of p_id for same[r-1] = I_r up[r] - q X_{r-1}:
-        //   R = sum_{f < id} g_same[r-1][f];  g_up[r][id] += p R;
-        //   d/dp = <R, up[r][id]> - 2 p sum_f <g_same[r-1][f], X_{r-1}[f]>
-        Acc<VEC> R;
-        R.zero();
-        float diag = 0.f;
-        for_faces(c, r, id, [&](int rr) {
-            const Vec<VEC> g = load_row<VEC>(g_same.p[r - 1], rr, c.lane);
-            const Vec<VEC> xf = load_row<VEC>(x.p[r - 1], rr, c.lane);
-            R.add(g);
-#pragma unroll
-            for (int k = 0; k < VEC; ++k) diag = fmaf(g.v[k], xf.v[k], diag);
-        });
-        const Vec<VEC> u = load_row<VEC>(up.p[r], row, c.lane);
-        gp += R.dot(u) - 2.0f * p * diag;
-        float add[VEC];
-#pragma unroll
-        for (int k = 0; k < VEC; ++k) add[k] = p * R.v[k];
-        add_row<VEC>(g_up.p[r], row, c.lane, add);
-    }
-    if (r == 2 && d.cnt[3] > 0) {
-        // same[3] = I_3^T down[2] - ...:  g_down[2][t] += sum_{s > t} p_s g_same[3][s]
-        Acc<VEC> acc;
-        acc.zero();
-        for_cofaces(c, 2, id, [&](int rr, float ps) { acc.fma(ps, load_row<VEC>(g_same.p[3], rr, c.lane)); });
-        add_row<VEC>(g_down.p[2], row, c.lane, acc.v);
-    }
-    if (r == 3) {
-        // direct p dependence of same[3] = p sum_t down[2][t] - c p^2 X3, and its diagonal
-        Acc<VEC> sum_d;
-        sum_d.zero();
-        const int n_faces = for_faces(c, 3, id, [&](int rr) { sum_d.add(load_row<VEC>(down.p[2], rr, c.lane)); });
-        const Vec<VEC> g = load_row<VEC>(g_same.p[3], row, c.lane);
-        const Vec<VEC> own = load_row<VEC>(x.p[3], row, c.lane);
-        const float cf = static_cast<float>(n_faces);
-        float d1 = 0.f, d2 = 0.f;
-#pragma unroll
-        for (int k = 0; k < VEC; ++k) {
-            d1 = fmaf(g.v[k], sum_d.v[k], d1);
-            d2 = fmaf(g.v[k], own.v[k], d2);
-            gx.v[k] = fmaf(-cf * p * p, g.v[k], gx.v[k]);
-        }
-        gp += d1 - 2.0f * cf * p * d2;
-    }
-
-    add_row<VEC>(g_x.p[r], row, c.lane, gx.v);
-    if (r >= 1) {
-        gp = warp_sum(gp);
-        if (c.lane == 0) g_probs[axis + d.off[r] + id] += gp;
-    }
-}
-
-// ------------------------------------------------------------------ backward, stage Y: cross-rank
-// With the TOTAL g_down / g_up:  down[r-1] = I_r X_r,  up[r] = I_r^T X_{r-1}.
-template <int VEC>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32) agg_cross_bwd(DeviceTables d, Sections sec,
-                                                                     topo_complex_view cv, Feat x, Feat g_down,
-                                                                     Feat g_up, FeatMut g_x,
-                                                                     float* __restrict__ g_probs) {
-    WarpCtx c;
-    int r, i, id;
-    if (!locate(d, sec, cv, &c, &r, &i, &id)) return;
-    const int row = c.ro[r] + i;
-    const long long axis = c.probs - cv.probs;
-    Acc<VEC> gx;
-    gx.zero();
-    float gp = 0.f;
-
-    if (r >= 1) {
-        const float p = c.prob(r, id);
-        // as the coface s of down[r-1]:  R = sum_f g_down[r-1][f];  g_x += p R;  d/dp = <R, X_r[s]>
-        // as the target of up[r]:        d/dp = <g_up[r][s], sum_f X_{r-1}[f]>
-        Acc<VEC> R, Q;
-        R.zero();
-        Q.zero();
-        for_faces(c, r, id, [&](int rr) {
-            R.add(load_row<VEC>(g_down.p[r - 1], rr, c.lane));
-            Q.add(load_row<VEC>(x.p[r - 1], rr, c.lane));
-        });
-        const Vec<VEC> own = load_row<VEC>(x.p[r], row, c.lane);
-        const Vec<VEC> gu = load_row<VEC>(g_up.p[r], row, c.lane);
-        gp = R.dot(own) + Q.dot(gu);
-#pragma unroll
-        for (int k = 0; k < VEC; ++k) gx.v[k] = p * R.v[k];
-    }
-    if (r < 3 && d.cnt[r + 1] > 0) {
-        // as a face of up[r+1]:  g_x[r][f] += sum_{s > f} p_s g_up[r+1][s]
-        for_cofaces(c, r, id, [&](int rr, float ps) { gx.fma(ps, load_row<VEC>(g_up.p[r + 1], rr, c.lane)); });
-    }
-    add_row<VEC>(g_x.p[r], row, c.lane, gx.v);
-    if (r >= 1) {
-        gp = warp_sum(gp);
-        if (c.lane == 0) g_probs[axis + d.off[r] + id] += gp;
-    }
-}
-
-// ------------------------------------------------------------------ generic CSR
 template <int VEC>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32) spmm_csr_kernel(long long rows, const int* __restrict__ row_ptr,
                                                                        const int* __restrict__ col_idx,
@@ -428,7 +577,10 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) spmm_csr_kernel(long long
                 acc.fma(vv, load_row<VEC>(x, cc, lane));
             }
         }
-        store_row<VEC>(y, static_cast<int>(row), lane, acc.v);
+        Vec<VEC> out;
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) out.v[k] = acc.v[k];
+        out.store(y + (row * 32 + lane) * VEC);
     }
 }
 
@@ -442,7 +594,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) sddmm_csr_kernel(long lon
     for (long long row = blockIdx.x * static_cast<long long>(kWarpsPerBlock) + (threadIdx.x >> 5); row < rows;
          row += static_cast<long long>(gridDim.x) * kWarpsPerBlock) {
         const int e0 = row_ptr[row], e1 = row_ptr[row + 1];
-        const Vec<VEC> g = load_row<VEC>(g_y, static_cast<int>(row), lane);
+        const Vec<VEC> g = load_row<VEC>(g_y, row, lane);
         for (int e = e0; e < e1; ++e) {
             const Vec<VEC> xv = load_row<VEC>(x, __ldg(col_idx + e), lane);
             float s = 0.f;
@@ -454,22 +606,21 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) sddmm_csr_kernel(long lon
     }
 }
 
-Sections make_sections(const DeviceTables& d, int64_t batch) {
+Sections make_sections(const DeviceTables& d, int64_t batch, int groups_per_block) {
     Sections s;
     int acc = 0;
     for (int r = 0; r < 4; ++r) {
         s.begin[r] = acc;
-        s.chunks[r] = (d.cnt[r] + kWarpsPerBlock - 1) / kWarpsPerBlock;
-        if (s.chunks[r] == 0) s.chunks[r] = 1;
+        s.chunks[r] = std::max(1, (d.cnt[r] + groups_per_block - 1) / groups_per_block);
         acc += (d.cnt[r] ? s.chunks[r] : 0) * static_cast<int>(batch);
     }
-    s.begin[4] = acc;
-    // empty ranks own no blocks: make their section empty but keep begin[] monotone
+    s.begin[4] = acc;   // empty (top) ranks own no blocks; begin[] stays monotone
     return s;
 }
 
 int check_view(const topo_tables* t, const topo_complex_view* cv, int channels) {
     TOPO_REQUIRE(t && cv, "null argument");
+    TOPO_REQUIRE(t->device >= 0, "tables were built host-only");
     TOPO_REQUIRE(cv->probs && cv->pos && cv->act_idx && cv->counts && cv->row_off, "null pointer in complex view");
     TOPO_REQUIRE(cv->batch >= 0 && cv->batch <= 65535, "batch out of range");
     if (channels != 32 && channels != 64 && channels != 128) {
@@ -484,8 +635,15 @@ int check_view(const topo_tables* t, const topo_complex_view* cv, int channels) 
 
 using namespace topo;
 
-#define DISPATCH_VEC(channels, CALL)      \
-    switch (channels) {                   \
+#define DISPATCH_LANES(channels, CALL)                  \
+    switch (channels) {                                 \
+        case 32: { constexpr int L = 8; CALL; } break;  \
+        case 64: { constexpr int L = 16; CALL; } break; \
+        default: { constexpr int L = 32; CALL; } break; \
+    }
+
+#define DISPATCH_VEC(channels, CALL)                      \
+    switch (channels) {                                   \
         case 32: { constexpr int VEC = 1; CALL; } break;  \
         case 64: { constexpr int VEC = 2; CALL; } break;  \
         default: { constexpr int VEC = 4; CALL; } break;  \
@@ -509,11 +667,11 @@ extern "C" int topo_sccn_aggregate_fwd(const topo_tables* t, const topo_complex_
             TOPO_REQUIRE(r == 3 || d.cnt[r + 1] == 0 || down[r], "missing down buffer");
         }
     }
-    const Sections sec = make_sections(d, cv->batch);
+    const Sections sec = make_sections(d, cv->batch, kThreads / (channels / 4));
     if (sec.begin[4] == 0) return TOPO_OK;
     cudaStream_t s = as_stream(stream);
-    DISPATCH_VEC(channels, (agg_cross_fwd<VEC><<<sec.begin[4], kWarpsPerBlock * 32, 0, s>>>(d, sec, *cv, fx, mdown, mup)));
-    DISPATCH_VEC(channels, (agg_same_fwd<VEC><<<sec.begin[4], kWarpsPerBlock * 32, 0, s>>>(d, sec, *cv, fx, fdown, fup, msame)));
+    DISPATCH_LANES(channels, (agg_cross_fwd<L><<<sec.begin[4], kThreads, 0, s>>>(d, sec, *cv, fx, mdown, mup)));
+    DISPATCH_LANES(channels, (agg_same_fwd<L><<<sec.begin[4], kThreads, 0, s>>>(d, sec, *cv, fx, fdown, fup, msame)));
     TOPO_LAUNCH_CHECK();
     return TOPO_OK;
 }
@@ -535,13 +693,13 @@ extern "C" int topo_sccn_aggregate_bwd(const topo_tables* t, const topo_complex_
         mgdown.p[r] = g_down[r]; mgup.p[r] = g_up[r]; mgx.p[r] = g_x[r];
         if (d.cnt[r]) TOPO_REQUIRE(x[r] && g_same[r] && g_x[r], "missing buffer for a populated rank");
     }
-    const Sections sec = make_sections(d, cv->batch);
+    const Sections sec = make_sections(d, cv->batch, kThreads / (channels / 4));
     if (sec.begin[4] == 0) return TOPO_OK;
     cudaStream_t s = as_stream(stream);
-    DISPATCH_VEC(channels, (agg_same_bwd<VEC><<<sec.begin[4], kWarpsPerBlock * 32, 0, s>>>(
-                               d, sec, *cv, fx, fdown, fup, fgsame, mgdown, mgup, mgx, g_probs)));
-    DISPATCH_VEC(channels, (agg_cross_bwd<VEC><<<sec.begin[4], kWarpsPerBlock * 32, 0, s>>>(
-                               d, sec, *cv, fx, fgdown, fgup, mgx, g_probs)));
+    DISPATCH_LANES(channels, (agg_same_bwd<L><<<sec.begin[4], kThreads, 0, s>>>(
+                                 d, sec, *cv, fx, fdown, fup, fgsame, mgdown, mgup, mgx, g_probs)));
+    DISPATCH_LANES(channels, (agg_cross_bwd<L><<<sec.begin[4], kThreads, 0, s>>>(
+                                 d, sec, *cv, fx, fgdown, fgup, mgx, g_probs)));
     TOPO_LAUNCH_CHECK();
     return TOPO_OK;
 }

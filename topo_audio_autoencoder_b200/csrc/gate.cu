@@ -159,7 +159,9 @@ __global__ void __launch_bounds__(256) binary_gumbel_fwd_kernel(const float* __r
     }
 }
 
-// d p0 / d l = p0 p1 (d a0/dl - d a1/dl) = 2 p0 p1 / T
+// Backward written in the order torch's autograd evaluates it (softmax backward over the pair, then the
+// division by temp, then stack([l, 1 - l])), so that the fp32 cancellation in (g - g p0) matches:
+//   d a0 = p0 (g - g p0),  d a1 = p1 (0 - g p0),  d l = d a0 / T - d a1 / T
 __global__ void __launch_bounds__(256) binary_gumbel_bwd_kernel(const float* __restrict__ logits,
                                                                  const float* __restrict__ gumbels, float temp,
                                                                  long long count, const float* __restrict__ grad_probs,
@@ -168,7 +170,11 @@ __global__ void __launch_bounds__(256) binary_gumbel_bwd_kernel(const float* __r
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < count; i += stride) {
         float p1;
         const float p0 = gumbel_prob(__ldg(logits + i), __ldg(gumbels + i), __ldg(gumbels + count + i), temp, &p1);
-        grad_logits[i] = __ldg(grad_probs + i) * (2.0f * p0 * p1 / temp);
+        const float g = __ldg(grad_probs + i);
+        const float dot = __fmul_rn(g, p0);
+        const float da0 = __fmul_rn(p0, __fsub_rn(g, dot));
+        const float da1 = __fmul_rn(p1, __fsub_rn(0.0f, dot));
+        grad_logits[i] = __fsub_rn(da0 / temp, da1 / temp);
     }
 }
 

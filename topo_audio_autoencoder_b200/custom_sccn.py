@@ -131,8 +131,9 @@ class _CombineFn(torch.autograd.Function):
         grads.g_att_w2, grads.g_att_b2 = ptr(g_w2), ptr(g_b2)
         grads.g_ln_gamma, grads.g_ln_beta = ptr(g_g), ptr(g_b)
         workspace = torch.empty(n_msgs * rows * ch, dtype=torch.float32, device=dev)
+        g_out = g_out.contiguous()     # named: a temporary would be freed before the launch reads it
         check(lib.topo_sccn_combine_bwd_attention(C.byref(params), rows, ptr(n_rows_dev, torch.int32),
-                                                  ptr(g_out.contiguous()), C.byref(grads), ptr(workspace), stream()))
+                                                  ptr(g_out), C.byref(grads), ptr(workspace), stream()))
         check(lib.topo_sccn_combine_bwd_conv(C.byref(params), rows, ptr(n_rows_dev, torch.int32), C.byref(grads),
                                              ptr(workspace), stream()))
         # finish the conv-weight chain: dW_k = scale_k P_k,  dscale_k = <W_k, P_k>

@@ -64,7 +64,8 @@ class _LayerNormFn(torch.autograd.Function):
         x, gamma = ctx.saved_tensors
         g_x = torch.empty_like(x)
         g_gamma, g_beta = torch.zeros_like(gamma), torch.zeros_like(gamma)
-        check(lib.topo_layernorm_bwd(x.shape[0], x.shape[1], ptr(x), ptr(gamma), ctx.eps, ptr(g_y.contiguous()),
+        g_y = g_y.contiguous()         # keep every buffer a launch reads alive in a named variable
+        check(lib.topo_layernorm_bwd(x.shape[0], x.shape[1], ptr(x), ptr(gamma), ctx.eps, ptr(g_y),
                                      ptr(g_x), ptr(g_gamma), ptr(g_beta), stream()))
         return g_x, g_gamma, g_beta, None
 
@@ -94,11 +95,13 @@ class _EmbedFn(torch.autograd.Function):
         cx, ch = ctx.cx, ctx.ch
         view = cx.view(probs)
         g_probs = torch.zeros_like(probs)
-        g_lnes = []
+        g_lnes, keep = [], []
         for r in range(4):
             g_l = torch.zeros_like(lnes[r])
             if g_xs[r] is not None and cx.rows_max[r]:
-                check(lib.topo_embed_bwd(cx.tables.handle, C.byref(view), r, ch, ptr(lnes[r]), ptr(g_xs[r].contiguous()),
+                g_x = g_xs[r].contiguous()
+                keep.append(g_x)
+                check(lib.topo_embed_bwd(cx.tables.handle, C.byref(view), r, ch, ptr(lnes[r]), ptr(g_x),
                                          ptr(g_l), ptr(g_probs), stream()))
             g_lnes.append(g_l)
         return (None, g_probs, *g_lnes)
@@ -121,9 +124,12 @@ class _PenaltiesFn(torch.autograd.Function):
         (probs,) = ctx.saved_tensors
         tables, lo, hi = ctx.cfg
         g = torch.empty_like(probs)
-        check(lib.topo_penalties_bwd(tables.handle, ptr(probs), probs.shape[0], lo, hi,
-                                     ptr(g_vp.contiguous()) if g_vp is not None else None,
-                                     ptr(g_ent.contiguous()) if g_ent is not None else None, ptr(g), stream()))
+        # both upstream gradients usually arrive as expanded (stride-0) tensors; their contiguous copies
+        # must outlive the launch, so they are bound to names (two inline temporaries would alias)
+        g_vp = g_vp.contiguous() if g_vp is not None else None
+        g_ent = g_ent.contiguous() if g_ent is not None else None
+        check(lib.topo_penalties_bwd(tables.handle, ptr(probs), probs.shape[0], lo, hi, ptr(g_vp), ptr(g_ent), ptr(g),
+                                     stream()))
         return g, None, None, None
 
 

@@ -106,8 +106,9 @@ class _BinaryGumbelFn(torch.autograd.Function):
     def backward(ctx, grad_probs):
         logits, gumbels = ctx.saved_tensors
         grad = torch.empty_like(logits)
+        grad_probs = grad_probs.contiguous()
         check(lib.topo_binary_gumbel_bwd(ptr(logits), ptr(gumbels), ctx.temp, logits.numel(),
-                                         ptr(grad_probs.contiguous()), ptr(grad), stream()))
+                                         ptr(grad_probs), ptr(grad), stream()))
         return grad, None, None
 
 
