@@ -248,6 +248,10 @@ typedef struct {
 
 int topo_sccn_combine_fwd(const topo_combine_params* p, int64_t rows, const int32_t* n_rows_dev,
                           float* out, topo_stream_t stream);
+/* Same contract, channels == 64 only: the GEMMs run on the tensor cores (tcgen05.mma kind::tf32, 3xTF32
+ * operand splitting for fp32-level accuracy, accumulators in tensor memory), 128-row tiles. */
+int topo_sccn_combine_fwd_tc(const topo_combine_params* p, int64_t rows, const int32_t* n_rows_dev,
+                             float* out, topo_stream_t stream);
 /* workspace: n_msgs * rows * C floats (dL/dm_k between the two backward kernels).
  * _attention: LayerNorm, softmax and attention-MLP backward -> dL/dm_k (workspace), g_x, attention and
  *             LayerNorm parameter gradients.  _conv: dL/dagg_k and g_wprod from the workspace.
@@ -262,6 +266,11 @@ int topo_sccn_combine_bwd_conv(const topo_combine_params* p, int64_t rows, const
 int topo_sccn_combine_bwd(const topo_combine_params* p, int64_t rows, const int32_t* n_rows_dev,
                           const float* grad_out, const topo_combine_grads* g, float* workspace,
                           topo_stream_t stream);
+
+/* Unit-test entry of the tensor-core path: out[rows, 64] = a[rows, 64] @ w[64, 64] evaluated with
+ * tcgen05.mma kind::tf32 and 3xTF32 operand splitting (the GEMM primitive of the combine kernels). */
+int topo_debug_gemm_tf32x3(const float* a, const float* w, int64_t rows, float* out,
+                           topo_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * D1-D3. Tiled pairwise spectral distance.  Replaces the pair loop of compute_distances

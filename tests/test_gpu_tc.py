@@ -1,0 +1,66 @@
+"""GPU: the tcgen05 (3xTF32) GEMM primitive against an fp64 matmul."""
+import pytest
+import torch
+
+from tests.helpers import report
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("rows", [1, 128, 1000, 20000])
+def test_tf32x3_gemm_is_fp32_accurate(rows):
+    from topo_audio_autoencoder_b200._lib import lib, check, ptr, stream
+    g = torch.Generator().manual_seed(rows)
+    a = (torch.randn(rows, 64, generator=g) * torch.logspace(-3, 3, 64)).cuda()     # wide dynamic range per column
+    w = torch.randn(64, 64, generator=g).cuda()
+    out = torch.full((rows, 64), float("nan"), device="cuda")
+    check(lib.topo_debug_gemm_tf32x3(ptr(a), ptr(w), rows, ptr(out), stream()))
+    torch.cuda.synchronize()
+    want64 = a.double() @ w.double()
+    fp32 = (a @ w).double()                       # cuBLAS fp32 (no TF32) as the accuracy yardstick
+    scale = (a.double().abs() @ w.double().abs())  # per-element condition scale sum|a||w|
+    ours = ((out.double() - want64).abs() / scale).max().item()
+    theirs = ((fp32 - want64).abs() / scale).max().item()
+    report(f"tc/gemm3xtf32/rows={rows}", out, want64.float())
+    assert torch.isfinite(out).all()
+    assert ours < 2e-6, f"relative-to-condition error {ours:.3e} (cuBLAS fp32: {theirs:.3e})"
+
+
+@pytest.mark.parametrize("n_msgs,apply_ln,rows", [(3, True, 1000), (2, False, 130), (1, True, 64), (3, True, 40000)])
+def test_tensor_core_combine_forward_matches_the_fp32_kernel(n_msgs, apply_ln, rows):
+    """The tcgen05 combine and the FFMA combine are two implementations of one contract."""
+    import ctypes as C
+    from topo_audio_autoencoder_b200._lib import lib, check, ptr, stream
+    from topo_audio_autoencoder_b200.custom_sccn import _make_params
+    from tests.helpers import assert_close
+    g = torch.Generator().manual_seed(rows + n_msgs)
+    ch = 64
+    rnd = lambda *s: torch.randn(*s, generator=g).cuda()     # noqa: E731
+    aggs = [rnd(rows, ch) * 2 for _ in range(n_msgs)]
+    ws = [rnd(ch, ch) * 0.2 for _ in range(n_msgs)]
+    scales = [torch.tensor([0.7 + 0.2 * k]).cuda() for k in range(n_msgs)]
+    x = rnd(rows, ch)
+    tensors = [rnd(ch, ch) * 0.2, rnd(ch) * 0.1, rnd(ch) * 0.3, rnd(1), 1 + 0.1 * rnd(ch), 0.1 * rnd(ch)]
+    params = _make_params(ch, n_msgs, aggs, ws, scales, x, tensors, 1e-5, apply_ln)
+    live = torch.tensor([rows - 3], dtype=torch.int32).cuda() if rows > 100 else None
+    outs = []
+    for fn in (lib.topo_sccn_combine_fwd, lib.topo_sccn_combine_fwd_tc):
+        out = torch.zeros(rows, ch, device="cuda")
+        check(fn(C.byref(params), rows, ptr(live, torch.int32), ptr(out), stream()))
+        torch.cuda.synchronize()
+        outs.append(out)
+    # fp64 reference of the same formula
+    m = [s.double() * (a.double() @ w.double()) + x.double() for a, w, s in zip(aggs, ws, scales)]
+    w1, b1, w2, b2, gam, bet = (t.double() for t in tensors)
+    sc = torch.stack([torch.nn.functional.gelu(mk @ w1.t() + b1) @ w2 + b2 for mk in m])
+    att = torch.softmax(sc, dim=0)
+    ref = sum(att[k].unsqueeze(1) * m[k] for k in range(n_msgs))
+    if apply_ln:
+        ref = torch.nn.functional.layer_norm(ref, (ch,), gam, bet, 1e-5)
+    n_live = rows - 3 if live is not None else rows
+    ref[n_live:] = 0
+    e_simt = (outs[0].double() - ref).abs().max().item()
+    e_tc = (outs[1].double() - ref).abs().max().item()
+    report(f"tc/combine-fwd/msgs={n_msgs}/ln={apply_ln}/rows={rows}", outs[1], outs[0])
+    assert e_tc <= 4 * e_simt + 1e-6, f"tensor-core error {e_tc:.3e} vs FFMA error {e_simt:.3e} (both against fp64)"
+    assert (outs[1][n_live:] == 0).all(), "rows past the live count must not be touched"

@@ -1,0 +1,162 @@
+// tcgen05 / TMEM / mbarrier primitives for sm_100a, written as inline PTX.
+//
+// Dense fp32-accurate GEMMs of the SCCN combine run on the 5th-generation tensor cores as
+// 3xTF32: every fp32 operand is split into a TF32 "hi" part and a TF32 "lo" residual,
+//     x = hi + lo,   hi = rna_tf32(x),   lo = x - hi   (exact in fp32)
+// and  A.B  ~=  A_lo.B_hi + A_hi.B_lo + A_hi.B_hi  is accumulated in fp32 in tensor memory.
+// The dropped A_lo.B_lo term is ~2^-22 relative, the same order as an fp32 FFMA chain's rounding.
+//
+// Operand tiles live in shared memory in the canonical K-major SWIZZLE_128B layout: rows of 128 bytes
+// (32 fp32), groups of 8 rows (1024 B, "swizzle atom"), the 16-byte chunk index XOR-ed with the row
+// index inside the atom; a 64-wide K extent is two such atoms.  The same bytes are also a valid
+// MN-major SWIZZLE_128B operand with the roles of rows and columns exchanged.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace topo {
+namespace tc {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// ---- mbarrier ------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol error traps (the launch fails) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > (1u << 26)) __trap();
+    }
+}
+
+// ---- proxy / tcgen05 fences ------------------------------------------------------------------
+// generic-proxy shared-memory writes -> visible to the async proxy (tcgen05.mma operand reads)
+__device__ __forceinline__ void fence_async_shared() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// ---- tensor memory ----------------------------------------------------------------------------
+// One full warp allocates `cols` (power of two >= 32) columns and publishes the base address in smem.
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_result, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "r"(cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t base, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(base), "r"(cols) : "memory");
+}
+
+// 32 lanes x 32 columns of fp32: thread i of the warp receives columns [col, col+32) of TMEM lane
+// (lane_base + i).  A warp may only touch the lane quarter 32*(warp_id % 4).
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// ---- descriptors --------------------------------------------------------------------------------
+// Shared-memory matrix descriptor, SWIZZLE_128B, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor:
+// start >> 4 in [0,14), LBO >> 4 in [16,30), SBO >> 4 in [32,46), version 1 in [46,48), layout in [61,64)).
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4) | (static_cast<uint64_t>(lbo_bytes >> 4) << 16) |
+           (static_cast<uint64_t>(sbo_bytes >> 4) << 32) | (static_cast<uint64_t>(1) << 46) |
+           (static_cast<uint64_t>(2) << 61);
+}
+
+// Instruction descriptor for kind::tf32, fp32 accumulate (cute::UMMA::InstrDescriptor).
+// a_mn / b_mn: 1 = the operand is MN-major, 0 = K-major.
+__host__ __device__ constexpr uint32_t idesc_tf32(int m, int n, int a_mn, int b_mn) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(a_mn) << 15) | (static_cast<uint32_t>(b_mn) << 16) |
+           (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
+}
+
+// D[tmem] (+)= A[smem] . B[smem]; issued by ONE thread.
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// All previously issued MMAs of this thread arrive on `bar` when complete (implies fence::before_thread_sync).
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// ---- 3xTF32 operand tiles --------------------------------------------------------------------------
+__device__ __forceinline__ float tf32_hi(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
+// Byte offset of the 16-byte chunk holding columns [4*chunk, 4*chunk+4) of `row` in a [rows x 64] fp32 tile
+// (two 32-column swizzle atoms, each rows*128 bytes).
+__device__ __forceinline__ uint32_t tile_chunk_offset(int rows, int row, int chunk /* 0..15 */) {
+    const int atom = chunk >> 3, c = chunk & 7;
+    return static_cast<uint32_t>(atom * rows * 128 + (row >> 3) * 1024 + (row & 7) * 128 + ((c ^ (row & 7)) << 4));
+}
+
+// Split four consecutive values and store them into the hi and lo tiles.
+__device__ __forceinline__ void store_split(uint8_t* hi_tile, uint8_t* lo_tile, int rows, int row, int chunk, float4 v) {
+    float4 h, l;
+    h.x = tf32_hi(v.x); h.y = tf32_hi(v.y); h.z = tf32_hi(v.z); h.w = tf32_hi(v.w);
+    l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
+    const uint32_t off = tile_chunk_offset(rows, row, chunk);
+    *reinterpret_cast<float4*>(hi_tile + off) = h;
+    *reinterpret_cast<float4*>(lo_tile + off) = l;
+}
+
+// D[128 x 64] (+)= A[128 x 64] . B^T with B stored as [64(N) x 64(K)], both K-major tiles; 3xTF32.
+// `first` = 0 overwrites D.  Issued by one thread: 24 MMAs of shape 128x64x8.
+__device__ __forceinline__ void gemm_128x64x64_3xtf32(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi,
+                                                      uint32_t b_lo, uint32_t accumulate_into) {
+    constexpr uint32_t idesc = idesc_tf32(128, 64, 0, 0);
+    uint32_t acc = accumulate_into;
+#pragma unroll
+    for (int pass = 0; pass < 3; ++pass) {       // small terms first
+        const uint32_t a = pass == 0 ? a_lo : a_hi;
+        const uint32_t b = pass == 1 ? b_lo : b_hi;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {            // 8 columns (32 B) per step; 4 steps per 128-B atom
+            const uint32_t a_off = (k >> 2) * (128 * 128) + (k & 3) * 32;
+            const uint32_t b_off = (k >> 2) * (64 * 128) + (k & 3) * 32;
+            mma_tf32(tmem_d, smem_desc_sw128(a + a_off, 16, 1024), smem_desc_sw128(b + b_off, 16, 1024), idesc, acc);
+            acc = 1;
+        }
+    }
+}
+
+}  // namespace tc
+}  // namespace topo

@@ -86,6 +86,11 @@ class _SpmmFn(torch.autograd.Function):
 # --------------------------------------------------------------------------------------------
 # fused message combine
 # --------------------------------------------------------------------------------------------
+# "tc": tcgen05 tensor-core kernels (3xTF32) where instantiated (channels == 64); "simt": the fp32 FFMA
+# kernels everywhere.  Both are hand-written CUDA behind the same C ABI; there is no PyTorch fallback.
+COMBINE_IMPL = "tc"
+
+
 class _CombineFn(torch.autograd.Function):
     """out = [LayerNorm] sum_k softmax_k(att(m_k)) m_k,  m_k = scale_k (agg_k @ W_k) + x."""
 
@@ -100,7 +105,8 @@ class _CombineFn(torch.autograd.Function):
                    ln_g.contiguous(), ln_b.contiguous()]
         params = _make_params(ch, n_msgs, aggs, ws, scales, x_c, tensors, ln_eps, apply_ln)
         out = torch.zeros(rows, ch, dtype=torch.float32, device=aggs[0].device)
-        check(lib.topo_sccn_combine_fwd(C.byref(params), rows, ptr(n_rows_dev, torch.int32), ptr(out), stream()))
+        fwd = lib.topo_sccn_combine_fwd_tc if (COMBINE_IMPL == "tc" and ch == 64) else lib.topo_sccn_combine_fwd
+        check(fwd(C.byref(params), rows, ptr(n_rows_dev, torch.int32), ptr(out), stream()))
         ctx.save_for_backward(x_c, n_rows_dev, *tensors, *aggs, *ws, *scales)
         ctx.cfg = (n_msgs, bool(apply_ln), float(ln_eps), x is not None)
         return out
