@@ -231,6 +231,12 @@ typedef struct {
     const float* ln_beta;    /* [C] */
     float ln_eps;
     int apply_ln;
+    /* Optional saved activations, one [rows, C] buffer per message (all NULL = not used).  The forward
+     * kernels WRITE them; topo_sccn_combine_bwd_attention READS them and then skips both recompute GEMMs:
+     *   saved_m[k]   = scale_k (agg_k W_k) + x          (the message)
+     *   saved_pre[k] = Linear1(m_k) = W1 m_k + b1       (pre-GELU attention hidden layer) */
+    float* saved_m[3];
+    float* saved_pre[3];
 } topo_combine_params;
 
 typedef struct {
@@ -267,9 +273,10 @@ int topo_sccn_combine_bwd(const topo_combine_params* p, int64_t rows, const int3
                           const float* grad_out, const topo_combine_grads* g, float* workspace,
                           topo_stream_t stream);
 
-/* Unit-test entry of the tensor-core path: out[rows, 64] = a[rows, 64] @ w[64, 64] evaluated with
- * tcgen05.mma kind::tf32 and 3xTF32 operand splitting (the GEMM primitive of the combine kernels). */
-int topo_debug_gemm_tf32x3(const float* a, const float* w, int64_t rows, float* out,
+/* Unit-test entry of the tensor-core path (tcgen05.mma kind::tf32, 3xTF32 operand splitting):
+ * out[rows, 64] = a[rows, 64] @ w[64, 64].  mode 0: both operands in shared memory (K-major SWIZZLE_128B);
+ * mode 3: the A operand in tensor memory (tcgen05.st by the row threads). */
+int topo_debug_gemm_tf32x3(const float* a, const float* w, int64_t rows, int mode, float* out,
                            topo_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------

@@ -14,7 +14,7 @@ def test_tf32x3_gemm_is_fp32_accurate(rows):
     a = (torch.randn(rows, 64, generator=g) * torch.logspace(-3, 3, 64)).cuda()     # wide dynamic range per column
     w = torch.randn(64, 64, generator=g).cuda()
     out = torch.full((rows, 64), float("nan"), device="cuda")
-    check(lib.topo_debug_gemm_tf32x3(ptr(a), ptr(w), rows, ptr(out), stream()))
+    check(lib.topo_debug_gemm_tf32x3(ptr(a), ptr(w), rows, 0, ptr(out), stream()))
     torch.cuda.synchronize()
     want64 = a.double() @ w.double()
     fp32 = (a @ w).double()                       # cuBLAS fp32 (no TF32) as the accuracy yardstick
@@ -64,3 +64,19 @@ def test_tensor_core_combine_forward_matches_the_fp32_kernel(n_msgs, apply_ln, r
     report(f"tc/combine-fwd/msgs={n_msgs}/ln={apply_ln}/rows={rows}", outs[1], outs[0])
     assert e_tc <= 4 * e_simt + 1e-6, f"tensor-core error {e_tc:.3e} vs FFMA error {e_simt:.3e} (both against fp64)"
     assert (outs[1][n_live:] == 0).all(), "rows past the live count must not be touched"
+
+
+def test_a_operand_from_tensor_memory():
+    """mode 3: the A operand of the MMA lives in tensor memory (written with tcgen05.st by the row threads)."""
+    from topo_audio_autoencoder_b200._lib import lib, check, ptr, stream
+    g = torch.Generator().manual_seed(9)
+    a = torch.randn(500, 64, generator=g).cuda()
+    w = torch.randn(64, 64, generator=g).cuda()
+    out = torch.full((500, 64), float("nan"), device="cuda")
+    check(lib.topo_debug_gemm_tf32x3(ptr(a), ptr(w), 500, 3, ptr(out), stream()))
+    torch.cuda.synchronize()
+    want = a.double() @ w.double()
+    scale = a.double().abs() @ w.double().abs()
+    err = ((out.double() - want).abs() / scale).max().item()
+    report("tc/gemm3xtf32/a-in-tmem", out, want.float())
+    assert err < 2e-6, err

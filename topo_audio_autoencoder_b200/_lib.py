@@ -34,7 +34,8 @@ class CombineParams(C.Structure):
                 ("x", C.c_void_p), ("att_w1", C.c_void_p), ("att_b1", C.c_void_p),
                 ("att_w2", C.c_void_p), ("att_b2", C.c_void_p),
                 ("ln_gamma", C.c_void_p), ("ln_beta", C.c_void_p),
-                ("ln_eps", C.c_float), ("apply_ln", C.c_int)]
+                ("ln_eps", C.c_float), ("apply_ln", C.c_int),
+                ("saved_m", C.c_void_p * 3), ("saved_pre", C.c_void_p * 3)]
 
 
 class CombineGrads(C.Structure):
@@ -84,7 +85,7 @@ SIGNATURES = {
     "topo_sccn_combine_bwd": [C.POINTER(CombineParams), _I64, _P, _P, C.POINTER(CombineGrads), _P, _P],
     "topo_sccn_combine_bwd_attention": [C.POINTER(CombineParams), _I64, _P, _P, C.POINTER(CombineGrads), _P, _P],
     "topo_sccn_combine_bwd_conv": [C.POINTER(CombineParams), _I64, _P, C.POINTER(CombineGrads), _P, _P],
-    "topo_debug_gemm_tf32x3": [_P, _P, _I64, _P, _P],
+    "topo_debug_gemm_tf32x3": [_P, _P, _I64, _I32, _P, _P],
     "topo_distance_padded_size": [C.POINTER(_I64), _I32],
     "topo_distance_prepare": [_P, _I64, _I64, C.POINTER(_I64), _I32, _F, _P, _P, _P, _P],
     "topo_distance_rows": [_P, _P, _P, _I64, C.POINTER(_I64), _I32, _I64, _I64, _I64, _I64, _P, _P],

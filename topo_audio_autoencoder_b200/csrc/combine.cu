@@ -265,6 +265,7 @@ __global__ void __launch_bounds__(NT) combine_fwd_kernel(topo_combine_params P, 
 #pragma unroll
                     for (int j = 0; j < CPT; ++j) m[k][i][j] = fmaf(scale[k], acc[i][j], xres[i][j]);
                 patch_to_tile<C>(Ms, tx, ty, m[k]);
+                if (P.saved_m[k] != nullptr) store_patch<C>(P.saved_m[k], row0, live, tx, ty, m[k]);
                 __syncthreads();
                 zero_acc<C>(acc);
                 gemm_nn<C>(Ms, W1t, acc, tx, ty);
@@ -274,10 +275,12 @@ __global__ void __launch_bounds__(NT) combine_fwd_kernel(topo_combine_params P, 
 #pragma unroll
                     for (int j = 0; j < CPT; ++j) {
                         const int col = tx * CPT + j;
-                        part = fmaf(gelu_exact(acc[i][j] + vecs[col]), vecs[C + col], part);
+                        acc[i][j] += vecs[col];                      // pre-GELU hidden activation
+                        part = fmaf(gelu_exact(acc[i][j]), vecs[C + col], part);
                     }
                     sc[i][k] = half_warp_sum(part) + b2;
                 }
+                if (P.saved_pre[k] != nullptr) store_patch<C>(P.saved_pre[k], row0, live, tx, ty, acc);
             } else {
 #pragma unroll
                 for (int i = 0; i < RPT; ++i) {
@@ -531,6 +534,191 @@ __global__ void __launch_bounds__(NT) combine_bwd_attn_kernel(topo_combine_param
 }
 
 // ---------------------------------------------------------------------------------------------
+// backward (1'), saved-activation variant: the forward left m_k and the pre-GELU hidden layer in HBM, so
+// neither the conv-weight GEMM nor the first attention GEMM is recomputed -- two GEMM-equivalents per
+// message (dpre W1 and the weight-gradient product dpre^T m_k) instead of five.
+// ---------------------------------------------------------------------------------------------
+template <int C>
+__global__ void __launch_bounds__(NT) combine_bwd_attn_saved_kernel(topo_combine_params P, long long rows,
+                                                                    const int* __restrict__ n_rows_dev,
+                                                                    const float* __restrict__ grad_out,
+                                                                    topo_combine_grads G, float* __restrict__ dm_ws) {
+    constexpr int CPT = Cfg<C>::CPT;
+    extern __shared__ __align__(16) float smem[];
+    float* W1n = smem;                         // [out][in] (as stored by nn.Linear)
+    float* vecs = W1n + C * C;                 // w2, gamma
+    float* Mk = vecs + 2 * C;                  // [3][TM][LD]
+    float* As = Mk + 3 * Cfg<C>::TILE;         // [TM][LD]
+    float* red = As + Cfg<C>::TILE;            // [4][C]
+
+    const long long live = n_rows_dev ? min(static_cast<long long>(*n_rows_dev), rows) : rows;
+    const long long tiles = (live + TM - 1) / TM;
+    if (blockIdx.x >= tiles) return;
+
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    load_matrix<C>(P.att_w1, W1n, false);
+    for (int c = threadIdx.x; c < C; c += NT) {
+        vecs[c] = __ldg(P.att_w2 + c);
+        vecs[C + c] = P.apply_ln ? __ldg(P.ln_gamma + c) : 1.f;
+    }
+    const float b2 = __ldg(P.att_b2);
+    float p_w1[RPT][CPT];
+    zero_acc<C>(p_w1);
+    float p_b1[CPT], p_w2[CPT], p_gamma[CPT], p_beta[CPT], p_b2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) p_b1[j] = p_w2[j] = p_gamma[j] = p_beta[j] = 0.f;
+    __syncthreads();
+
+    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const long long row0 = tile * TM;
+        float sc[RPT][3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            if (k < P.n_msgs) {
+                load_tile<C>(P.saved_m[k], row0, live, Mk + k * Cfg<C>::TILE);
+                float pre[RPT][CPT];
+                load_patch<C>(P.saved_pre[k], row0, live, tx, ty, pre);
+#pragma unroll
+                for (int i = 0; i < RPT; ++i) {
+                    float part = 0.f;
+#pragma unroll
+                    for (int j = 0; j < CPT; ++j) part = fmaf(gelu_exact(pre[i][j]), vecs[tx * CPT + j], part);
+                    sc[i][k] = half_warp_sum(part) + b2;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < RPT; ++i) sc[i][k] = 0.f;
+            }
+        }
+        __syncthreads();                               // the message tiles are in shared memory
+
+        float dmix[RPT][CPT];
+        load_patch<C>(grad_out, row0, live, tx, ty, dmix);
+        float att[RPT][3], dsc[RPT][3];
+#pragma unroll
+        for (int i = 0; i < RPT; ++i) {
+            const Softmax3 a = softmax_msgs(sc[i], P.n_msgs);
+            float mk[3][CPT];
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+#pragma unroll
+                for (int j = 0; j < CPT; ++j)
+                    mk[k][j] = (k < P.n_msgs) ? Mk[k * Cfg<C>::TILE + (ty * RPT + i) * Cfg<C>::LD + tx * CPT + j] : 0.f;
+            if (P.apply_ln) {
+                float mix[CPT], sum = 0.f;
+#pragma unroll
+                for (int j = 0; j < CPT; ++j) {
+                    mix[j] = a.a[0] * mk[0][j] + a.a[1] * mk[1][j] + a.a[2] * mk[2][j];
+                    sum += mix[j];
+                }
+                const float mean = half_warp_sum(sum) * (1.0f / C);
+                float var = 0.f;
+#pragma unroll
+                for (int j = 0; j < CPT; ++j) var = fmaf(mix[j] - mean, mix[j] - mean, var);
+                const float rstd = 1.0f / sqrtf(half_warp_sum(var) * (1.0f / C) + P.ln_eps);
+                float c1 = 0.f, c2 = 0.f, xh[CPT], gy[CPT];
+#pragma unroll
+                for (int j = 0; j < CPT; ++j) {
+                    xh[j] = (mix[j] - mean) * rstd;
+                    p_gamma[j] = fmaf(dmix[i][j], xh[j], p_gamma[j]);
+                    p_beta[j] += dmix[i][j];
+                    gy[j] = dmix[i][j] * vecs[C + tx * CPT + j];
+                    c1 += gy[j];
+                    c2 = fmaf(gy[j], xh[j], c2);
+                }
+                c1 = half_warp_sum(c1) * (1.0f / C);
+                c2 = half_warp_sum(c2) * (1.0f / C);
+#pragma unroll
+                for (int j = 0; j < CPT; ++j) dmix[i][j] = rstd * (gy[j] - c1 - xh[j] * c2);
+            }
+            float da[3], dot = 0.f;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                float part = 0.f;
+#pragma unroll
+                for (int j = 0; j < CPT; ++j) part = fmaf(dmix[i][j], mk[k][j], part);
+                da[k] = half_warp_sum(part);
+                dot = fmaf(a.a[k], da[k], dot);
+            }
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                att[i][k] = a.a[k];
+                dsc[i][k] = a.a[k] * (da[k] - dot);
+                if (tx == 0 && k < P.n_msgs) p_b2 += dsc[i][k];
+            }
+        }
+
+        float dxres[RPT][CPT];
+        zero_acc<C>(dxres);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            if (k < P.n_msgs) {
+                const float* Mt = Mk + k * Cfg<C>::TILE;
+                float acc[RPT][CPT];
+                load_patch<C>(P.saved_pre[k], row0, live, tx, ty, acc);
+#pragma unroll
+                for (int i = 0; i < RPT; ++i)
+#pragma unroll
+                    for (int j = 0; j < CPT; ++j) {
+                        const float pre = acc[i][j];
+                        p_w2[j] = fmaf(dsc[i][k], gelu_exact(pre), p_w2[j]);
+                        const float dpre = dsc[i][k] * vecs[tx * CPT + j] * gelu_exact_grad(pre);
+                        p_b1[j] += dpre;
+                        acc[i][j] = dpre;
+                    }
+                __syncthreads();                       // previous readers of As are done
+                patch_to_tile<C>(As, tx, ty, acc);
+                __syncthreads();
+                zero_acc<C>(acc);
+                gemm_nn<C>(As, W1n, acc, tx, ty);      // dpre @ W1  ([o][in])
+#pragma unroll
+                for (int i = 0; i < RPT; ++i)
+#pragma unroll
+                    for (int j = 0; j < CPT; ++j) {
+                        acc[i][j] = fmaf(att[i][k], dmix[i][j], acc[i][j]);
+                        dxres[i][j] += acc[i][j];
+                    }
+                store_patch<C>(dm_ws + static_cast<long long>(k) * rows * C, row0, live, tx, ty, acc);
+                gemm_tn<C>(As, Mt, p_w1, tx, ty);      // dW1 += dpre^T m_k
+            }
+        }
+        if (G.g_x != nullptr) store_patch<C>(G.g_x, row0, live, tx, ty, dxres);
+        __syncthreads();
+    }
+
+#pragma unroll
+    for (int i = 0; i < RPT; ++i)
+#pragma unroll
+        for (int j = 0; j < CPT; ++j)
+            if (ty * RPT < C) atomicAdd(G.g_att_w1 + (ty * RPT + i) * C + tx * CPT + j, p_w1[i][j]);
+    __syncthreads();
+    float* scratch = Mk;
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) {
+        const int col = tx * CPT + j;
+        scratch[(ty * 4 + 0) * C + col] = p_b1[j];
+        scratch[(ty * 4 + 1) * C + col] = p_w2[j];
+        scratch[(ty * 4 + 2) * C + col] = p_gamma[j];
+        scratch[(ty * 4 + 3) * C + col] = p_beta[j];
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < 4 * C; idx += NT) {
+        const int which = idx / C, col = idx % C;
+        float s = 0.f;
+        for (int g = 0; g < 16; ++g) s += scratch[(g * 4 + which) * C + col];
+        red[idx] = s;
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < 4 * C; idx += NT) {
+        const int which = idx / C, col = idx % C;
+        float* dst = which == 0 ? G.g_att_b1 : (which == 1 ? G.g_att_w2 : (which == 2 ? G.g_ln_gamma : G.g_ln_beta));
+        if (dst != nullptr && (which < 2 || P.apply_ln)) atomicAdd(dst + col, red[idx]);
+    }
+    p_b2 = warp_sum(p_b2);
+    if ((threadIdx.x & 31) == 0 && p_b2 != 0.f) atomicAdd(G.g_att_b2, p_b2);
+}
+
+// ---------------------------------------------------------------------------------------------
 // backward (2): through the conv weight, one message per blockIdx.y
 //   dL/dagg_k = scale_k (dL/dm_k) W_k^T ;  g_wprod[k] += agg_k^T (dL/dm_k)
 // ---------------------------------------------------------------------------------------------
@@ -740,8 +928,7 @@ int check_combine(const topo_combine_params* p, int64_t rows) {
 
 template <typename K>
 int set_smem(K kernel, size_t bytes) {
-    TOPO_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes)));
-    return TOPO_OK;
+    return ensure_dynamic_smem(reinterpret_cast<const void*>(kernel), bytes);
 }
 
 template <int C>
@@ -750,6 +937,8 @@ template <int C>
 size_t bwd_attn_smem() { return sizeof(float) * (5 * C * C + 4 * C + 4 * Cfg<C>::TILE + 4 * C); }
 template <int C>
 size_t bwd_conv_smem() { return sizeof(float) * (C * C + 2 * Cfg<C>::TILE); }
+template <int C>
+size_t bwd_attn_saved_smem() { return sizeof(float) * (C * C + 2 * C + 4 * Cfg<C>::TILE + 4 * C); }
 
 }  // namespace
 }  // namespace topo
@@ -797,6 +986,21 @@ extern "C" int topo_sccn_combine_bwd_attention(const topo_combine_params* p, int
     if (rows == 0) return TOPO_OK;
     const int tiles = static_cast<int>((rows + TM - 1) / TM);
     cudaStream_t s = as_stream(stream);
+    bool saved = true;
+    for (int k = 0; k < p->n_msgs; ++k) saved = saved && p->saved_m[k] && p->saved_pre[k];
+    if (saved) {
+        if (p->channels == 64) {
+            if (int rc = set_smem(combine_bwd_attn_saved_kernel<64>, bwd_attn_saved_smem<64>())) return rc;
+            combine_bwd_attn_saved_kernel<64><<<std::min(tiles, sm_count() * 2), NT, bwd_attn_saved_smem<64>(), s>>>(
+                *p, rows, n_rows_dev, grad_out, *g, workspace);
+        } else {
+            if (int rc = set_smem(combine_bwd_attn_saved_kernel<32>, bwd_attn_saved_smem<32>())) return rc;
+            combine_bwd_attn_saved_kernel<32><<<std::min(tiles, sm_count() * 4), NT, bwd_attn_saved_smem<32>(), s>>>(
+                *p, rows, n_rows_dev, grad_out, *g, workspace);
+        }
+        TOPO_LAUNCH_CHECK();
+        return TOPO_OK;
+    }
     if (p->channels == 64) {
         if (int rc = set_smem(combine_bwd_attn_kernel<64>, bwd_attn_smem<64>())) return rc;
         combine_bwd_attn_kernel<64><<<std::min(tiles, sm_count()), NT, bwd_attn_smem<64>(), s>>>(

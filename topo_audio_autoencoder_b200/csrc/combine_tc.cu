@@ -35,11 +35,46 @@ __device__ __forceinline__ void load_weight_tiles(const float* __restrict__ w, b
     }
 }
 
-// out[rows, 64] = a[rows, 64] @ w[64, 64]   (debug / unit-test entry for the tcgen05 path)
+// One 3xTF32 product with explicit operand descriptors: `steps` MMAs of K = 8 each per pass; operand k-step
+// offsets and LBO/SBO are given by the caller (K-major and MN-major operands differ only there).
+struct OperandWalk {
+    uint32_t hi, lo;        // shared-memory addresses of the hi / lo tile images
+    uint32_t step_bytes;    // advance per k-step inside a group of `steps_per_jump`
+    uint32_t jump_bytes;    // advance per group
+    uint32_t steps_per_jump;
+    uint32_t lbo, sbo;
+};
+__device__ __forceinline__ void gemm_3xtf32(uint32_t tmem_d, const OperandWalk& a, const OperandWalk& b, uint32_t idesc,
+                                            int steps, uint32_t accumulate_into) {
+    uint32_t acc = accumulate_into;
+#pragma unroll 1
+    for (int pass = 0; pass < 3; ++pass) {
+        const uint32_t a_base = pass == 0 ? a.lo : a.hi;
+        const uint32_t b_base = pass == 1 ? b.lo : b.hi;
+#pragma unroll 1
+        for (int k = 0; k < steps; ++k) {
+            const uint32_t ao = (k / a.steps_per_jump) * a.jump_bytes + (k % a.steps_per_jump) * a.step_bytes;
+            const uint32_t bo = (k / b.steps_per_jump) * b.jump_bytes + (k % b.steps_per_jump) * b.step_bytes;
+            mma_tf32(tmem_d, smem_desc_sw128(a_base + ao, a.lbo, a.sbo), smem_desc_sw128(b_base + bo, b.lbo, b.sbo), idesc, acc);
+            acc = 1;
+        }
+    }
+}
+// A [rows x 64] tile image contracted over its 64 columns (K-major): 4 steps of 32 B per 128-B atom, 2 atoms.
+__device__ __forceinline__ OperandWalk walk_k_major(uint32_t hi, uint32_t lo, int rows) {
+    return OperandWalk{hi, lo, 32u, static_cast<uint32_t>(rows) * 128u, 4u, 16u, 1024u};
+}
+// Debug / unit-test entry for the tcgen05 path: out[rows, 64] = a[rows, 64] @ w[64, 64].
+//   mode 0: both operands from shared memory (K-major SWIZZLE_128B tiles)
+//   mode 3: the A operand from tensor memory (written by the row threads with tcgen05.st)
+// (MN-major fp32 operands need the SWIZZLE_128B_BASE32B layout, a different shared-memory image; the
+//  weight-gradient products that would use them stay on the FFMA path for now.)
 __global__ void __launch_bounds__(128) debug_gemm_kernel(const float* __restrict__ a, const float* __restrict__ w,
-                                                         long long rows, float* __restrict__ out) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+                                                         long long rows, int mode, float* __restrict__ out) {
+    // 1024-byte aligned by declaration (SWIZZLE_128B atoms); no pointer arithmetic through integers, so the
+    // compiler keeps every access in the shared address space (LDS/STS, not generic LD/ST)
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* base = smem_raw;
     uint8_t* a_hi = base;
     uint8_t* a_lo = a_hi + kATile;
     uint8_t* b_hi = a_lo + kATile;
@@ -52,7 +87,7 @@ __global__ void __launch_bounds__(128) debug_gemm_kernel(const float* __restrict
         mbar_init(&bar, 1);
         fence_barrier_init();
     }
-    if (warp == 0) tmem_alloc(&tmem_base_smem, 64);
+    if (warp == 0) tmem_alloc(&tmem_base_smem, 256);
     load_weight_tiles(w, true, b_hi, b_lo, tid, 128);
     tc_fence_before_sync();
     __syncthreads();
@@ -70,11 +105,44 @@ __global__ void __launch_bounds__(128) debug_gemm_kernel(const float* __restrict
             if (row0 + r < rows) v = __ldg(reinterpret_cast<const float4*>(a + (row0 + r) * kC) + chunk);
             store_split(a_hi, a_lo, kTileRows, r, chunk, v);
         }
+        if (mode == 3) {
+            // A operand in tensor memory: thread t owns lane t; hi in columns [64,128), lo in [128,192)
+            const long long arow = row0 + tid;
+            for (int c8 = 0; c8 < 8; ++c8) {
+                float hi8[8], lo8[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float x = arow < rows ? __ldg(a + arow * kC + c8 * 8 + i) : 0.f;
+                    hi8[i] = tf32_hi(x);
+                    lo8[i] = x - hi8[i];
+                }
+                const uint32_t lane = tmem_base_smem + (static_cast<uint32_t>(warp * 32) << 16);
+                tmem_st8(lane + 64 + c8 * 8, hi8);
+                tmem_st8(lane + 128 + c8 * 8, lo8);
+            }
+            tmem_st_wait();
+            tc_fence_before_sync();
+        }
         fence_async_shared();
         __syncthreads();
         if (tid == 0) {
             tc_fence_after_sync();
-            gemm_128x64x64_3xtf32(tmem_base, smem_u32(a_hi), smem_u32(a_lo), smem_u32(b_hi), smem_u32(b_lo), 0);
+            if (mode == 3) {
+                uint32_t acc = 0;
+                for (int pass = 0; pass < 3; ++pass) {
+                    const uint32_t a_col = pass == 0 ? 128 : 64;
+                    const uint32_t bb = smem_u32(pass == 1 ? b_lo : b_hi);
+                    for (int k = 0; k < 8; ++k) {
+                        const uint32_t bo = (k >> 2) * (kC * 128) + (k & 3) * 32;
+                        mma_tf32_ta(tmem_base, tmem_base + a_col + k * 8, smem_desc_sw128(bb + bo, 16, 1024),
+                                    idesc_tf32(128, 64, 0, 0), acc);
+                        acc = 1;
+                    }
+                }
+            } else {
+                gemm_3xtf32(tmem_base, walk_k_major(smem_u32(a_hi), smem_u32(a_lo), kTileRows),
+                            walk_k_major(smem_u32(b_hi), smem_u32(b_lo), kC), idesc_tf32(128, 64, 0, 0), 8, 0);
+            }
             mma_commit(&bar);
         }
         mbar_wait(&bar, parity);
@@ -96,37 +164,46 @@ __global__ void __launch_bounds__(128) debug_gemm_kernel(const float* __restrict
         tc_fence_before_sync();
         __syncthreads();
     }
-    if (warp == 0) tmem_dealloc(tmem_base, 64);
+    if (warp == 0) tmem_dealloc(tmem_base, 256);
 }
 
 
 // ---------------------------------------------------------------------------------------------
-// Fused combine forward on tensor cores (C = 64).  256 threads: warps 0-3 are "row threads" (thread t
-// owns tile row t == TMEM lane t and runs the epilogues), warps 4-7 are "loader threads" (stream the
-// aggregate tiles global -> registers -> split -> swizzled shared memory, one message ahead); thread 128
-// issues every MMA.  Tensor memory: T_k (conv outputs, 3 x 64 columns, kept for the final mix) and H
-// (attention hidden layer, 64 columns).  Per message:
-//     MMA1  T_k = agg_k W_k                    (24 x tcgen05.mma 128x64x8)
-//     epi1  m_k = scale_k T_k + x  -> A operand (row threads, TMEM -> registers -> smem)
+// Fused combine forward on tensor cores (C = 64), 128-row tiles, 256 threads.
+// Thread (h, r) = (tid / 128, tid % 128) owns columns [32h, 32h + 32) of tile row r (TMEM lane r; both
+// warp groups reach the same lane quarter, warp % 4).  Everybody loads, everybody runs epilogues; thread 0
+// issues the MMAs.  Tensor memory: T_k (conv outputs, 3 x 64 columns, kept for the final mix) and H
+// (attention hidden layer, 64 columns).  Per message k:
+//     stage A = agg_k (prefetched one message ahead into registers, split hi/lo, swizzled)
+//     MMA1  T_k = agg_k W_k                    (24 x tcgen05.mma 128x64x8, 3xTF32)
+//     epi1  m_k = scale_k T_k + x  -> A operand (TMEM -> registers -> smem)
 //     MMA2  H   = m_k W1^T
-//     epi2  s_k = w2 . GELU(H + b1) + b2
-// then  out = sum_k softmax(s)_k scale_k T_k + x,  LayerNorm,  store.
+//     epi2  s_k = w2 . GELU(H + b1) + b2       (half-row partials combined through shared memory)
+// then  out = (sum a_k) x + sum_k a_k scale_k T_k,  LayerNorm,  store.
+// The message loop and the 8-column epilogue chunks are real loops: the fully unrolled first version
+// spent 19-35 % of its issue slots on instruction-cache misses (profiles/r01_combine_fwd_tc_v1.md).
 // ---------------------------------------------------------------------------------------------
 struct FwdSmem {
     static constexpr uint32_t kWeights = 0;                       // [4][hi, lo] x 16 KB
     static constexpr uint32_t kA = 8 * kBTile;                    // hi, lo x 32 KB
     static constexpr uint32_t kVecs = kA + 2 * kATile;            // b1, w2, gamma, beta
-    static constexpr uint32_t kTotal = kVecs + 4 * kC * 4;
+    static constexpr uint32_t kRed = kVecs + 4 * kC * 4;          // [2][128] half-row partials
+    static constexpr uint32_t kScale = kRed + 2 * kTileRows * 4;  // scale[3], b2
+    static constexpr uint32_t kTotal = kScale + 16;
 };
 
 __global__ void __launch_bounds__(256, 1) combine_fwd_tc_kernel(topo_combine_params P, long long rows,
                                                                 const int* __restrict__ n_rows_dev,
                                                                 float* __restrict__ out) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // 1024-byte aligned by declaration (SWIZZLE_128B atoms); no pointer arithmetic through integers, so the
+    // compiler keeps every access in the shared address space (LDS/STS, not generic LD/ST)
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* base = smem_raw;
     uint8_t* a_hi = base + FwdSmem::kA;
     uint8_t* a_lo = a_hi + kATile;
     float* vecs = reinterpret_cast<float*>(base + FwdSmem::kVecs);
+    float* red = reinterpret_cast<float*>(base + FwdSmem::kRed);
+    float* scale_s = reinterpret_cast<float*>(base + FwdSmem::kScale);
     __shared__ uint64_t bar;
     __shared__ uint32_t tmem_base_smem;
 
@@ -135,8 +212,7 @@ __global__ void __launch_bounds__(256, 1) combine_fwd_tc_kernel(topo_combine_par
     if (blockIdx.x >= tiles) return;
 
     const int tid = threadIdx.x, warp = tid >> 5;
-    const bool is_row = tid < 128;
-    const int lt = tid & 127;                       // index inside the role group
+    const int h = tid >> 7, r = tid & 127, col0 = h * 32;
     const int n_msgs = P.n_msgs;
 
     if (tid == 0) {
@@ -153,182 +229,174 @@ __global__ void __launch_bounds__(256, 1) combine_fwd_tc_kernel(topo_combine_par
         vecs[2 * kC + c] = P.apply_ln ? __ldg(P.ln_gamma + c) : 1.f;
         vecs[3 * kC + c] = P.apply_ln ? __ldg(P.ln_beta + c) : 0.f;
     }
-    float scale[3];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) scale[k] = k < n_msgs ? __ldg(P.scale[k]) : 0.f;
-    const float b2 = __ldg(P.att_b2);
+    if (tid < 3) scale_s[tid] = tid < n_msgs ? __ldg(P.scale[tid]) : 0.f;
+    if (tid == 3) scale_s[3] = __ldg(P.att_b2);
     fence_async_shared();
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem_base = tmem_base_smem;
-    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16) + col0;
     const uint32_t a_hi_s = smem_u32(a_hi), a_lo_s = smem_u32(a_lo), w_s = smem_u32(base);
+    const float b2 = scale_s[3];
     uint32_t parity = 0;
 
-    // 64 registers with a role-dependent meaning: loader threads keep 16 prefetched chunks of the next
-    // aggregate tile in them, row threads keep their x row (and accumulate the output row into it)
-    float4 buf[16];
+    float4 pre[8];      // the next aggregate tile, 8 of its 2048 16-byte chunks per thread
     auto prefetch = [&](const float* __restrict__ src, long long row0) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const int idx = j * 128 + lt, r = idx >> 4, chunk = idx & 15;
-            buf[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (row0 + r < live) buf[j] = __ldg(reinterpret_cast<const float4*>(src + (row0 + r) * kC) + chunk);
+        for (int j = 0; j < 8; ++j) {
+            const int idx = j * 256 + tid, rr = idx >> 4, chunk = idx & 15;
+            pre[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (row0 + rr < live) pre[j] = __ldg(reinterpret_cast<const float4*>(src + (row0 + rr) * kC) + chunk);
         }
     };
-    if (!is_row) prefetch(P.agg[0], static_cast<long long>(blockIdx.x) * kTileRows);
+    prefetch(P.agg[0], static_cast<long long>(blockIdx.x) * kTileRows);
 
     for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
         const long long row0 = tile * kTileRows;
-        const long long row = row0 + lt;
-        float sc[3] = {0.f, 0.f, 0.f};
-        if (is_row) {
+        const long long row = row0 + r;
+        float4 xr[8];   // this thread's half of the residual row; later the output accumulator
 #pragma unroll
-            for (int q = 0; q < 16; ++q) {
-                buf[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (P.x != nullptr && row < live) buf[q] = __ldg(reinterpret_cast<const float4*>(P.x + row * kC) + q);
-            }
+        for (int q = 0; q < 8; ++q) {
+            xr[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (P.x != nullptr && row < live) xr[q] = __ldg(reinterpret_cast<const float4*>(P.x + row * kC + col0) + q);
         }
+        float sc0 = 0.f, sc1 = 0.f, sc2 = 0.f;
+#pragma unroll 1
+        for (int k = 0; k < n_msgs; ++k) {
+            const float scale_k = scale_s[k];
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            if (k >= n_msgs) break;
-            if (!is_row) {
-                // stage the prefetched aggregate tile as the A operand, then start fetching the next one
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int idx = j * 128 + lt;
-                    store_split(a_hi, a_lo, kTileRows, idx >> 4, idx & 15, buf[j]);
-                }
-                fence_async_shared();
-                if (k + 1 < n_msgs) prefetch(P.agg[k + 1], row0);
-                else if (tile + gridDim.x < tiles) prefetch(P.agg[0], (tile + gridDim.x) * kTileRows);
+            for (int j = 0; j < 8; ++j) {
+                const int idx = j * 256 + tid;
+                store_split(a_hi, a_lo, kTileRows, idx >> 4, idx & 15, pre[j]);
             }
+            fence_async_shared();
+            if (k + 1 < n_msgs) prefetch(P.agg[k + 1], row0);
+            else if (tile + gridDim.x < tiles) prefetch(P.agg[0], (tile + gridDim.x) * kTileRows);
             __syncthreads();                                                    // S1: A = agg_k is staged
-            if (tid == 128) {
+            if (tid == 0) {
                 tc_fence_after_sync();
                 gemm_128x64x64_3xtf32(tmem_base + k * kC, a_hi_s, a_lo_s, w_s + (2 * k) * kBTile, w_s + (2 * k + 1) * kBTile, 0);
                 mma_commit(&bar);
             }
-            if (is_row) {
-                mbar_wait(&bar, parity);
-                tc_fence_after_sync();
-                // epilogue 1: m_k = scale_k T_k + x, re-staged as the A operand of the attention GEMM
-#pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    float v[32];
-                    tmem_ld32(lane_addr + k * kC + half * 32, v);
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const float4 xr = buf[half * 8 + q];
-                        float4 m;
-                        m.x = fmaf(scale[k], v[q * 4 + 0], xr.x);
-                        m.y = fmaf(scale[k], v[q * 4 + 1], xr.y);
-                        m.z = fmaf(scale[k], v[q * 4 + 2], xr.z);
-                        m.w = fmaf(scale[k], v[q * 4 + 3], xr.w);
-                        store_split(a_hi, a_lo, kTileRows, lt, half * 8 + q, m);
-                    }
-                }
-                fence_async_shared();
-                tc_fence_before_sync();
-            }
+            mbar_wait(&bar, parity);
             parity ^= 1;
+            tc_fence_after_sync();
+            // epilogue 1: m_k = scale_k T_k + x, re-staged as the A operand of the attention GEMM
+#pragma unroll
+            for (int c8 = 0; c8 < 4; ++c8) {
+                float v[8];
+                tmem_ld8(lane_addr + k * kC + c8 * 8, v);
+                const float4 x0 = xr[c8 * 2], x1 = xr[c8 * 2 + 1];
+                const float4 m0 = make_float4(fmaf(scale_k, v[0], x0.x), fmaf(scale_k, v[1], x0.y), fmaf(scale_k, v[2], x0.z),
+                                              fmaf(scale_k, v[3], x0.w));
+                const float4 m1 = make_float4(fmaf(scale_k, v[4], x1.x), fmaf(scale_k, v[5], x1.y), fmaf(scale_k, v[6], x1.z),
+                                              fmaf(scale_k, v[7], x1.w));
+                store_split(a_hi, a_lo, kTileRows, r, h * 8 + c8 * 2, m0);
+                store_split(a_hi, a_lo, kTileRows, r, h * 8 + c8 * 2 + 1, m1);
+                if (P.saved_m[k] != nullptr && row < live) {
+                    float4* dst = reinterpret_cast<float4*>(P.saved_m[k] + row * kC + col0) + c8 * 2;
+                    dst[0] = m0;
+                    dst[1] = m1;
+                }
+            }
+            fence_async_shared();
+            tc_fence_before_sync();
             __syncthreads();                                                    // S2: A = m_k is staged
-            if (tid == 128) {
+            if (tid == 0) {
                 tc_fence_after_sync();
                 gemm_128x64x64_3xtf32(tmem_base + 3 * kC, a_hi_s, a_lo_s, w_s + 6 * kBTile, w_s + 7 * kBTile, 0);
                 mma_commit(&bar);
             }
-            if (is_row) {
-                mbar_wait(&bar, parity);
-                tc_fence_after_sync();
-                // epilogue 2: attention score of this message
-                float s = 0.f;
-#pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    float v[32];
-                    tmem_ld32(lane_addr + 3 * kC + half * 32, v);
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const int col = half * 32 + i;
-                        s = fmaf(gelu_exact(v[i] + vecs[col]), vecs[kC + col], s);
-                    }
-                }
-                sc[k] = s + b2;
-                tc_fence_before_sync();
-            }
+            mbar_wait(&bar, parity);
             parity ^= 1;
-            __syncthreads();                                                    // S3: A and H are free again
-        }
-        if (is_row) {
-            // softmax over the messages, mix straight from tensor memory, LayerNorm, store
-            float mx = sc[0];
-            for (int k = 1; k < n_msgs; ++k) mx = fmaxf(mx, sc[k]);
-            float a[3], sum = 0.f;
+            tc_fence_after_sync();
+            // epilogue 2: this half-row's share of the attention score
+            float s = 0.f;
+#pragma unroll 1
+            for (int c8 = 0; c8 < 4; ++c8) {
+                float v[8];
+                tmem_ld8(lane_addr + 3 * kC + c8 * 8, v);
+                const float* b1p = vecs + col0 + c8 * 8;
+                const float* w2p = vecs + kC + col0 + c8 * 8;
 #pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                a[k] = k < n_msgs ? expf(sc[k] - mx) : 0.f;
-                sum += a[k];
-            }
-            // out = (sum_k a_k) x + sum_k (a_k scale_k) T_k, accumulated in place over the x registers
-            float asum = 0.f, coef[3];
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                const float ak = a[k] / sum;
-                asum += ak;
-                coef[k] = ak * scale[k];
-            }
-#pragma unroll
-            for (int q = 0; q < 16; ++q) {
-                buf[q].x *= asum; buf[q].y *= asum; buf[q].z *= asum; buf[q].w *= asum;
-            }
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                if (k < n_msgs) {
-#pragma unroll
-                    for (int half = 0; half < 2; ++half) {
-                        float v[32];
-                        tmem_ld32(lane_addr + k * kC + half * 32, v);
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            float4& o = buf[half * 8 + q];
-                            o.x = fmaf(coef[k], v[q * 4 + 0], o.x);
-                            o.y = fmaf(coef[k], v[q * 4 + 1], o.y);
-                            o.z = fmaf(coef[k], v[q * 4 + 2], o.z);
-                            o.w = fmaf(coef[k], v[q * 4 + 3], o.w);
-                        }
-                    }
+                for (int i = 0; i < 8; ++i) {
+                    v[i] += b1p[i];                                   // pre-GELU hidden activation
+                    s = fmaf(gelu_exact(v[i]), w2p[i], s);
+                }
+                if (P.saved_pre[k] != nullptr && row < live) {
+                    float4* dst = reinterpret_cast<float4*>(P.saved_pre[k] + row * kC + col0) + c8 * 2;
+                    dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+                    dst[1] = make_float4(v[4], v[5], v[6], v[7]);
                 }
             }
+            red[h * kTileRows + r] = s;
             tc_fence_before_sync();
-            if (P.apply_ln) {
-                float mean = 0.f;
+            __syncthreads();                                                    // S3: A, H and `red` are consistent
+            const float score = red[r] + red[kTileRows + r] + b2;
+            if (k == 0) sc0 = score; else if (k == 1) sc1 = score; else sc2 = score;
+        }
+        // softmax over the messages, mix straight from tensor memory
+        float mx = sc0;
+        if (n_msgs > 1) mx = fmaxf(mx, sc1);
+        if (n_msgs > 2) mx = fmaxf(mx, sc2);
+        const float e0 = expf(sc0 - mx), e1 = n_msgs > 1 ? expf(sc1 - mx) : 0.f, e2 = n_msgs > 2 ? expf(sc2 - mx) : 0.f;
+        const float esum = e0 + e1 + e2;
+        const float a0 = e0 / esum, a1 = e1 / esum, a2 = e2 / esum;
+        const float asum = a0 + a1 + a2;
 #pragma unroll
-                for (int q = 0; q < 16; ++q) mean += (buf[q].x + buf[q].y) + (buf[q].z + buf[q].w);
-                mean *= (1.0f / kC);
-                float var = 0.f;
+        for (int q = 0; q < 8; ++q) {
+            xr[q].x *= asum; xr[q].y *= asum; xr[q].z *= asum; xr[q].w *= asum;
+        }
 #pragma unroll
-                for (int q = 0; q < 16; ++q) {
-                    var = fmaf(buf[q].x - mean, buf[q].x - mean, var);
-                    var = fmaf(buf[q].y - mean, buf[q].y - mean, var);
-                    var = fmaf(buf[q].z - mean, buf[q].z - mean, var);
-                    var = fmaf(buf[q].w - mean, buf[q].w - mean, var);
-                }
-                const float rstd = 1.0f / sqrtf(var * (1.0f / kC) + P.ln_eps);
+        for (int k = 0; k < 3; ++k) {
+            if (k < n_msgs) {
+                const float coef = (k == 0 ? a0 : (k == 1 ? a1 : a2)) * scale_s[k];
 #pragma unroll
-                for (int q = 0; q < 16; ++q) {
-                    const float* gm = vecs + 2 * kC + q * 4;
-                    const float* bt = vecs + 3 * kC + q * 4;
-                    buf[q].x = fmaf((buf[q].x - mean) * rstd, gm[0], bt[0]);
-                    buf[q].y = fmaf((buf[q].y - mean) * rstd, gm[1], bt[1]);
-                    buf[q].z = fmaf((buf[q].z - mean) * rstd, gm[2], bt[2]);
-                    buf[q].w = fmaf((buf[q].w - mean) * rstd, gm[3], bt[3]);
+                for (int c8 = 0; c8 < 4; ++c8) {
+                    float v[8];
+                    tmem_ld8(lane_addr + k * kC + c8 * 8, v);
+                    float4& o0 = xr[c8 * 2];
+                    float4& o1 = xr[c8 * 2 + 1];
+                    o0.x = fmaf(coef, v[0], o0.x); o0.y = fmaf(coef, v[1], o0.y); o0.z = fmaf(coef, v[2], o0.z); o0.w = fmaf(coef, v[3], o0.w);
+                    o1.x = fmaf(coef, v[4], o1.x); o1.y = fmaf(coef, v[5], o1.y); o1.z = fmaf(coef, v[6], o1.z); o1.w = fmaf(coef, v[7], o1.w);
                 }
             }
-            if (row < live) {
+        }
+        tc_fence_before_sync();
+        if (P.apply_ln) {
+            float part = 0.f;
 #pragma unroll
-                for (int q = 0; q < 16; ++q) *reinterpret_cast<float4*>(out + row * kC + q * 4) = buf[q];
+            for (int q = 0; q < 8; ++q) part += (xr[q].x + xr[q].y) + (xr[q].z + xr[q].w);
+            __syncthreads();                       // every thread has consumed the last score from `red`
+            red[h * kTileRows + r] = part;
+            __syncthreads();
+            const float mean = (red[r] + red[kTileRows + r]) * (1.0f / kC);
+            float var = 0.f;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                var = fmaf(xr[q].x - mean, xr[q].x - mean, var);
+                var = fmaf(xr[q].y - mean, xr[q].y - mean, var);
+                var = fmaf(xr[q].z - mean, xr[q].z - mean, var);
+                var = fmaf(xr[q].w - mean, xr[q].w - mean, var);
             }
+            __syncthreads();
+            red[h * kTileRows + r] = var;
+            __syncthreads();
+            const float rstd = 1.0f / sqrtf((red[r] + red[kTileRows + r]) * (1.0f / kC) + P.ln_eps);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const float* gm = vecs + 2 * kC + col0 + q * 4;
+                const float* bt = vecs + 3 * kC + col0 + q * 4;
+                xr[q].x = fmaf((xr[q].x - mean) * rstd, gm[0], bt[0]);
+                xr[q].y = fmaf((xr[q].y - mean) * rstd, gm[1], bt[1]);
+                xr[q].z = fmaf((xr[q].z - mean) * rstd, gm[2], bt[2]);
+                xr[q].w = fmaf((xr[q].w - mean) * rstd, gm[3], bt[3]);
+            }
+        }
+        if (row < live) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) *(reinterpret_cast<float4*>(out + row * kC + col0) + q) = xr[q];
         }
     }
     tc_fence_before_sync();
@@ -341,13 +409,15 @@ __global__ void __launch_bounds__(256, 1) combine_fwd_tc_kernel(topo_combine_par
 
 using namespace topo;
 
-extern "C" int topo_debug_gemm_tf32x3(const float* a, const float* w, int64_t rows, float* out, topo_stream_t stream) {
+extern "C" int topo_debug_gemm_tf32x3(const float* a, const float* w, int64_t rows, int mode, float* out,
+                                      topo_stream_t stream) {
     TOPO_REQUIRE(a && w && out && rows >= 0, "bad argument");
+    TOPO_REQUIRE(mode == 0 || mode == 3, "mode must be 0 (operands in shared memory) or 3 (A in tensor memory)");
     if (rows == 0) return TOPO_OK;
-    const size_t smem = 2 * kATile + 2 * kBTile + 1024;
-    TOPO_CUDA(cudaFuncSetAttribute(debug_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    const size_t smem = 2 * kATile + 2 * kBTile;
+    if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(debug_gemm_kernel), smem)) return rc;
     const int tiles = static_cast<int>((rows + kTileRows - 1) / kTileRows);
-    debug_gemm_kernel<<<std::min(tiles, sm_count()), 128, smem, as_stream(stream)>>>(a, w, rows, out);
+    debug_gemm_kernel<<<std::min(tiles, sm_count()), 128, smem, as_stream(stream)>>>(a, w, rows, mode, out);
     TOPO_LAUNCH_CHECK();
     return TOPO_OK;
 }
@@ -365,7 +435,7 @@ extern "C" int topo_sccn_combine_fwd_tc(const topo_combine_params* p, int64_t ro
     TOPO_REQUIRE(!p->apply_ln || (p->ln_gamma && p->ln_beta), "null LayerNorm parameter");
     if (rows == 0) return TOPO_OK;
     const size_t smem = FwdSmem::kTotal + 1024;
-    TOPO_CUDA(cudaFuncSetAttribute(combine_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(combine_fwd_tc_kernel), smem)) return rc;
     const int tiles = static_cast<int>((rows + kTileRows - 1) / kTileRows);
     combine_fwd_tc_kernel<<<std::min(tiles, sm_count()), 256, smem, as_stream(stream)>>>(*p, rows, n_rows_dev, out);
     TOPO_LAUNCH_CHECK();

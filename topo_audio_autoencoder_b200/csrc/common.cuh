@@ -35,6 +35,8 @@ void set_error(const std::string& msg);
 static inline cudaStream_t as_stream(topo_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
 int sm_count();
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per kernel (never again, e.g. not inside a graph capture)
+int ensure_dynamic_smem(const void* kernel, size_t bytes);
 
 constexpr int kMaxRank = 3;
 

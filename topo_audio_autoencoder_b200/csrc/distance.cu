@@ -252,8 +252,7 @@ extern "C" int topo_distance_rows(const float* spec_p, const float* logspec_p, c
     const Segments seg = make_segments(seg_len, n_scales);
     const dim3 grid(static_cast<unsigned>((col_end - col_begin + TJ - 1) / TJ),
                     static_cast<unsigned>((row_end - row_begin + TI - 1) / TI));
-    TOPO_CUDA(cudaFuncSetAttribute(distance_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   static_cast<int>(2 * sizeof(Stage))));
+    if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(distance_rows_kernel), 2 * sizeof(Stage))) return rc;
     distance_rows_kernel<<<grid, 256, 2 * sizeof(Stage), as_stream(stream)>>>(
         spec_p, logspec_p, sq_mean, n, seg, row_begin, row_end, col_begin, col_end, out);
     TOPO_LAUNCH_CHECK();

@@ -4,6 +4,8 @@
 // combinatorial-number-system rank instead of a linear search, and the dense 0/1 matrices are
 // only materialised on request.
 #include <algorithm>
+#include <map>
+#include <mutex>
 #include <utility>
 
 #include "common.cuh"
@@ -22,6 +24,17 @@ int sm_count() {
         if (cached <= 0) cached = 148;
     }
     return cached;
+}
+
+int ensure_dynamic_smem(const void* kernel, size_t bytes) {
+    static std::mutex mu;
+    static std::map<const void*, size_t> done;
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = done.find(kernel);
+    if (it != done.end() && it->second >= bytes) return TOPO_OK;
+    TOPO_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes)));
+    done[kernel] = bytes;
+    return TOPO_OK;
 }
 
 namespace {

@@ -8,8 +8,9 @@
 //
 // Operand tiles live in shared memory in the canonical K-major SWIZZLE_128B layout: rows of 128 bytes
 // (32 fp32), groups of 8 rows (1024 B, "swizzle atom"), the 16-byte chunk index XOR-ed with the row
-// index inside the atom; a 64-wide K extent is two such atoms.  The same bytes are also a valid
-// MN-major SWIZZLE_128B operand with the roles of rows and columns exchanged.
+// index inside the atom; a 64-wide K extent is two such atoms.  The A operand may instead live in tensor
+// memory (lane = row, column = k), written by the threads that own the rows with tcgen05.st.
+// (MN-major fp32 operands would need SWIZZLE_128B_BASE32B, a different image; not used.)
 #pragma once
 
 #include <cuda_runtime.h>
@@ -84,6 +85,27 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// 32 lanes x 8 columns (small code footprint for looped epilogues)
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// registers -> tensor memory, 32 lanes x 8 columns
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
+                 "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+                 "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 // ---- descriptors --------------------------------------------------------------------------------
 // Shared-memory matrix descriptor, SWIZZLE_128B, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor:
 // start >> 4 in [0,14), LBO >> 4 in [16,30), SBO >> 4 in [32,46), version 1 in [46,48), layout in [61,64)).
@@ -107,6 +129,15 @@ __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint6
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// Same with the A operand in tensor memory (128 lanes x 8 columns of 32-bit values per MMA).
+__device__ __forceinline__ void mma_tf32_ta(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
 // All previously issued MMAs of this thread arrive on `bar` when complete (implies fence::before_thread_sync).

@@ -89,13 +89,16 @@ class _SpmmFn(torch.autograd.Function):
 # "tc": tcgen05 tensor-core kernels (3xTF32) where instantiated (channels == 64); "simt": the fp32 FFMA
 # kernels everywhere.  Both are hand-written CUDA behind the same C ABI; there is no PyTorch fallback.
 COMBINE_IMPL = "tc"
+# keep m_k and the pre-GELU attention layer from the forward (2 x n_msgs x rows x C floats per call) so the
+# backward does not recompute two of its five GEMMs per message
+SAVE_ACTIVATIONS = True
 
 
 class _CombineFn(torch.autograd.Function):
     """out = [LayerNorm] sum_k softmax_k(att(m_k)) m_k,  m_k = scale_k (agg_k @ W_k) + x."""
 
     @staticmethod
-    def forward(ctx, n_msgs, apply_ln, ln_eps, n_rows_dev, x, att_w1, att_b1, att_w2, att_b2, ln_g, ln_b, *rest):
+    def forward(ctx, n_msgs, apply_ln, ln_eps, n_rows_dev, zero_dead_rows, x, att_w1, att_b1, att_w2, att_b2, ln_g, ln_b, *rest):
         aggs = [t.contiguous() for t in rest[:n_msgs]]
         ws = [t.contiguous() for t in rest[n_msgs:2 * n_msgs]]
         scales = [t.contiguous() for t in rest[2 * n_msgs:3 * n_msgs]]
@@ -103,11 +106,20 @@ class _CombineFn(torch.autograd.Function):
         x_c = x.contiguous() if x is not None else None
         tensors = [att_w1.contiguous(), att_b1.contiguous(), att_w2.contiguous(), att_b2.contiguous(),
                    ln_g.contiguous(), ln_b.contiguous()]
-        params = _make_params(ch, n_msgs, aggs, ws, scales, x_c, tensors, ln_eps, apply_ln)
-        out = torch.zeros(rows, ch, dtype=torch.float32, device=aggs[0].device)
+        dev = aggs[0].device
+        saved = None
+        if SAVE_ACTIVATIONS and any(ctx.needs_input_grad):
+            # the messages and the pre-GELU attention layer, kept for the backward (skips both recompute GEMMs)
+            saved = ([torch.empty(rows, ch, dtype=torch.float32, device=dev) for _ in range(n_msgs)],
+                     [torch.empty(rows, ch, dtype=torch.float32, device=dev) for _ in range(n_msgs)])
+        params = _make_params(ch, n_msgs, aggs, ws, scales, x_c, tensors, ln_eps, apply_ln, saved)
+        # rows past the live count are never read by any kernel; they are zero-filled only where the tensor is
+        # handed to the caller (last layer), so that padded buffers are safe to reduce over
+        out = (torch.zeros if zero_dead_rows else torch.empty)(rows, ch, dtype=torch.float32, device=dev)
         fwd = lib.topo_sccn_combine_fwd_tc if (COMBINE_IMPL == "tc" and ch == 64) else lib.topo_sccn_combine_fwd
         check(fwd(C.byref(params), rows, ptr(n_rows_dev, torch.int32), ptr(out), stream()))
         ctx.save_for_backward(x_c, n_rows_dev, *tensors, *aggs, *ws, *scales)
+        ctx.saved_act = saved
         ctx.cfg = (n_msgs, bool(apply_ln), float(ln_eps), x is not None)
         return out
 
@@ -121,9 +133,9 @@ class _CombineFn(torch.autograd.Function):
         scales = list(saved[8 + 2 * n_msgs:8 + 3 * n_msgs])
         rows, ch = aggs[0].shape
         dev = aggs[0].device
-        params = _make_params(ch, n_msgs, aggs, ws, scales, x_c, tensors, ln_eps, apply_ln)
-        g_aggs = [torch.zeros(rows, ch, dtype=torch.float32, device=dev) for _ in range(n_msgs)]
-        g_x = torch.zeros(rows, ch, dtype=torch.float32, device=dev) if has_x else None
+        params = _make_params(ch, n_msgs, aggs, ws, scales, x_c, tensors, ln_eps, apply_ln, ctx.saved_act)
+        g_aggs = [torch.empty(rows, ch, dtype=torch.float32, device=dev) for _ in range(n_msgs)]
+        g_x = torch.empty(rows, ch, dtype=torch.float32, device=dev) if has_x else None
         wprod = [torch.zeros(ch, ch, dtype=torch.float32, device=dev) for _ in range(n_msgs)]
         g_w1, g_b1 = torch.zeros_like(tensors[0]), torch.zeros_like(tensors[1])
         g_w2, g_b2 = torch.zeros_like(tensors[2]), torch.zeros_like(tensors[3])
@@ -145,17 +157,19 @@ class _CombineFn(torch.autograd.Function):
         # finish the conv-weight chain: dW_k = scale_k P_k,  dscale_k = <W_k, P_k>
         g_ws = [wprod[k] * scales[k] for k in range(n_msgs)]
         g_ss = [(wprod[k] * ws[k]).sum().reshape(scales[k].shape) for k in range(n_msgs)]
-        return (None, None, None, None, g_x, g_w1, g_b1, g_w2, g_b2,
+        return (None, None, None, None, None, g_x, g_w1, g_b1, g_w2, g_b2,
                 g_g if apply_ln else None, g_b if apply_ln else None, *g_aggs, *g_ws, *g_ss)
 
 
-def _make_params(ch, n_msgs, aggs, ws, scales, x, tensors, ln_eps, apply_ln) -> CombineParams:
+def _make_params(ch, n_msgs, aggs, ws, scales, x, tensors, ln_eps, apply_ln, saved=None) -> CombineParams:
     p = CombineParams()
     p.channels, p.n_msgs = ch, n_msgs
     for k in range(3):
         p.agg[k] = ptr(aggs[k]) if k < n_msgs else None
         p.w[k] = ptr(ws[k]) if k < n_msgs else None
         p.scale[k] = ptr(scales[k]) if k < n_msgs else None
+        p.saved_m[k] = ptr(saved[0][k]) if (saved is not None and k < n_msgs) else None
+        p.saved_pre[k] = ptr(saved[1][k]) if (saved is not None and k < n_msgs) else None
     p.x = ptr(x)
     p.att_w1, p.att_b1, p.att_w2, p.att_b2 = (ptr(t) for t in tensors[:4])
     p.ln_gamma, p.ln_beta = ptr(tensors[4]), ptr(tensors[5])
@@ -204,8 +218,14 @@ class _AggregateFn(torch.autograd.Function):
         probs = probs.contiguous()
         ch = xs[0].shape[1]
         dev = probs.device
-        new = lambda r: torch.zeros(cx.rows_max[r], ch, dtype=torch.float32, device=dev)   # noqa: E731
-        down = [new(0), new(1), new(2), None]
+        counts = cx.tables.counts
+
+        def new(r, source_rank=None):
+            # every live row is written by the kernel; an aggregate whose source rank does not exist is all zero
+            empty_source = source_rank is not None and counts[source_rank] == 0
+            return (torch.zeros if empty_source else torch.empty)(cx.rows_max[r], ch, dtype=torch.float32, device=dev)
+
+        down = [new(0, 1), new(1, 2), new(2, 3), None]
         up = [None, new(1), new(2), new(3)]
         same = [new(r) for r in range(4)]
         view = cx.view(probs)
@@ -280,11 +300,11 @@ class GradientSCCNLayer(nn.Module):
 
     # -- shared tail: messages -> output rows --------------------------------------------------
     def _combine(self, key: str, x: torch.Tensor, msgs: Sequence[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]],
-                 n_rows_dev: Optional[torch.Tensor] = None) -> torch.Tensor:
+                 n_rows_dev: Optional[torch.Tensor] = None, zero_dead_rows: bool = True) -> torch.Tensor:
         att, ln = self.message_attention[key], self.layer_norms[key]
         apply_ln = self.training and not self.is_final_layer                                               # :133-134
         aggs, ws, scales = zip(*msgs)
-        return _CombineFn.apply(len(msgs), apply_ln, ln.eps, n_rows_dev, x if self.residual else None,
+        return _CombineFn.apply(len(msgs), apply_ln, ln.eps, n_rows_dev, zero_dead_rows, x if self.residual else None,
                                 att[0].weight, att[0].bias, att[2].weight.reshape(-1), att[2].bias,
                                 ln.weight, ln.bias, *aggs, *ws, *scales)
 
@@ -329,7 +349,7 @@ class GradientSCCNLayer(nn.Module):
         return out
 
     # -- batch of complexes, matrix-free --------------------------------------------------------
-    def forward_complex(self, cx: BatchedComplex, xs: Sequence[torch.Tensor]) -> List[torch.Tensor]:
+    def forward_complex(self, cx: BatchedComplex, xs: Sequence[torch.Tensor], zero_dead_rows: bool = True) -> List[torch.Tensor]:
         if self.max_rank != 3:
             raise ValueError("forward_complex is built for the reference's max_rank = 3 complexes")
         d0, d1, d2, u1, u2, u3, s0, s1, s2, s3 = _AggregateFn.apply(cx, cx.probs, *xs)
@@ -343,7 +363,7 @@ class GradientSCCNLayer(nn.Module):
                 msgs.append((down[r], self.convs_high_to_low[key].weight, sc["high_to_low"]))
             if r > 0:
                 msgs.append((up[r], self.convs_low_to_high[key].weight, sc["low_to_high"]))
-            out.append(self._combine(key, xs[r], msgs, cx.live_rows(r)) if cx.rows_max[r] else xs[r])
+            out.append(self._combine(key, xs[r], msgs, cx.live_rows(r), zero_dead_rows) if cx.rows_max[r] else xs[r])
         return out
 
 
@@ -367,6 +387,6 @@ class GradientSCCN(nn.Module):
         return features
 
     def forward_complex(self, cx: BatchedComplex, xs: Sequence[torch.Tensor]) -> List[torch.Tensor]:
-        for layer in self.layers:
-            xs = layer.forward_complex(cx, xs)
+        for i, layer in enumerate(self.layers):
+            xs = layer.forward_complex(cx, xs, zero_dead_rows=(i == len(self.layers) - 1))
         return list(xs)

@@ -81,7 +81,7 @@ class _EmbedFn(torch.autograd.Function):
         view = cx.view(probs)
         outs = []
         for r in range(4):
-            x = torch.zeros(cx.rows_max[r], ch, dtype=torch.float32, device=probs.device)
+            x = torch.empty(cx.rows_max[r], ch, dtype=torch.float32, device=probs.device)   # live rows are all written
             if cx.rows_max[r]:
                 check(lib.topo_embed_fwd(cx.tables.handle, C.byref(view), r, ch, ptr(lnes[r]), ptr(x), stream()))
             outs.append(x)
