@@ -272,6 +272,12 @@ int topo_sccn_combine_bwd_conv(const topo_combine_params* p, int64_t rows, const
 int topo_sccn_combine_bwd(const topo_combine_params* p, int64_t rows, const int32_t* n_rows_dev,
                           const float* grad_out, const topo_combine_grads* g, float* workspace,
                           topo_stream_t stream);
+/* topo_sccn_combine_bwd_conv on the tensor cores (channels == 64): both the input gradient and the
+ * weight-gradient product (a contraction over rows, staged as transposed K-major tiles) are 3xTF32
+ * tcgen05 GEMMs; the 64 x 64 product accumulates in tensor memory across the CTA's tiles. */
+int topo_sccn_combine_bwd_conv_tc(const topo_combine_params* p, int64_t rows,
+                                  const int32_t* n_rows_dev, const topo_combine_grads* g,
+                                  const float* workspace, topo_stream_t stream);
 
 /* Unit-test entry of the tensor-core path (tcgen05.mma kind::tf32, 3xTF32 operand splitting):
  * out[rows, 64] = a[rows, 64] @ w[64, 64].  mode 0: both operands in shared memory (K-major SWIZZLE_128B);

@@ -80,3 +80,44 @@ def test_a_operand_from_tensor_memory():
     err = ((out.double() - want).abs() / scale).max().item()
     report("tc/gemm3xtf32/a-in-tmem", out, want.float())
     assert err < 2e-6, err
+
+
+@pytest.mark.parametrize("n_msgs,rows", [(3, 1000), (2, 130), (1, 64), (3, 40000)])
+def test_tensor_core_conv_backward_matches_the_fp32_kernel(n_msgs, rows):
+    """dL/dagg_k and the weight-gradient product agg_k^T dL/dm_k: tcgen05 kernel vs FFMA kernel vs fp64."""
+    import ctypes as C
+    from topo_audio_autoencoder_b200._lib import lib, check, ptr, stream, CombineGrads
+    from topo_audio_autoencoder_b200.custom_sccn import _make_params
+    g = torch.Generator().manual_seed(rows * 7 + n_msgs)
+    ch = 64
+    rnd = lambda *s: torch.randn(*s, generator=g).cuda()     # noqa: E731
+    aggs = [rnd(rows, ch) for _ in range(n_msgs)]
+    ws = [rnd(ch, ch) * 0.2 for _ in range(n_msgs)]
+    scales = [torch.tensor([0.7 + 0.2 * k]).cuda() for k in range(n_msgs)]
+    tensors = [rnd(ch, ch), rnd(ch), rnd(ch), rnd(1), rnd(ch), rnd(ch)]
+    params = _make_params(ch, n_msgs, aggs, ws, scales, None, tensors, 1e-5, False)
+    dm = rnd(n_msgs, rows, ch).contiguous()
+    live_n = rows - 3 if rows > 100 else rows
+    live = torch.tensor([live_n], dtype=torch.int32).cuda()
+    results = []
+    for fn in (lib.topo_sccn_combine_bwd_conv, lib.topo_sccn_combine_bwd_conv_tc):
+        g_aggs = [torch.zeros(rows, ch, device="cuda") for _ in range(n_msgs)]
+        wprod = [torch.zeros(ch, ch, device="cuda") for _ in range(n_msgs)]
+        grads = CombineGrads()
+        for k in range(n_msgs):
+            grads.g_agg[k], grads.g_wprod[k] = ptr(g_aggs[k]), ptr(wprod[k])
+        check(fn(C.byref(params), rows, ptr(live, torch.int32), C.byref(grads), ptr(dm), stream()))
+        torch.cuda.synchronize()
+        results.append((g_aggs, wprod))
+    for k in range(n_msgs):
+        d = dm[k, :live_n].double()
+        want_g = scales[k].double() * (d @ ws[k].double().t())
+        cond_g = scales[k].double().abs() * (d.abs() @ ws[k].double().abs().t())
+        want_p = aggs[k][:live_n].double().t() @ d
+        cond_p = aggs[k][:live_n].double().abs().t() @ d.abs()
+        for name, idx, want, cond, sl in (("g_agg", 0, want_g, cond_g, slice(0, live_n)), ("wprod", 1, want_p, cond_p, slice(None))):
+            tcv = results[1][idx][k][sl].double()
+            err = ((tcv - want).abs() / cond).max().item()        # relative to sum |a||b|, like the GEMM primitive
+            report(f"tc/conv-bwd/{name}/msgs={n_msgs}/rows={rows}/k={k}", tcv.float(), want.float())
+            assert err < 2e-6, (name, k, err)
+        assert (results[1][0][k][live_n:] == 0).all()

@@ -152,8 +152,8 @@ class _CombineFn(torch.autograd.Function):
         g_out = g_out.contiguous()     # named: a temporary would be freed before the launch reads it
         check(lib.topo_sccn_combine_bwd_attention(C.byref(params), rows, ptr(n_rows_dev, torch.int32),
                                                   ptr(g_out), C.byref(grads), ptr(workspace), stream()))
-        check(lib.topo_sccn_combine_bwd_conv(C.byref(params), rows, ptr(n_rows_dev, torch.int32), C.byref(grads),
-                                             ptr(workspace), stream()))
+        conv = lib.topo_sccn_combine_bwd_conv_tc if (COMBINE_IMPL == "tc" and ch == 64) else lib.topo_sccn_combine_bwd_conv
+        check(conv(C.byref(params), rows, ptr(n_rows_dev, torch.int32), C.byref(grads), ptr(workspace), stream()))
         # finish the conv-weight chain: dW_k = scale_k P_k,  dscale_k = <W_k, P_k>
         g_ws = [wprod[k] * scales[k] for k in range(n_msgs)]
         g_ss = [(wprod[k] * ws[k]).sum().reshape(scales[k].shape) for k in range(n_msgs)]
