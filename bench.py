@@ -231,6 +231,7 @@ def algorithmic_bytes_per_call(name, counts, ch, n_layers):
 def run_ours(args):
     import torch.distributed as dist
     import topo_audio_autoencoder_b200 as T
+    from topo_audio_autoencoder_b200.dist import allreduce_gradients
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -283,13 +284,7 @@ def run_ours(args):
         else:
             out, lg = eager_step(lg, nz)
         if world > 1:
-            flat = torch.cat([p.grad.reshape(-1) for p in params])
-            dist.all_reduce(flat)
-            flat.div_(world)
-            o = 0
-            for p in params:
-                p.grad.copy_(flat[o:o + p.numel()].view_as(p.grad))
-                o += p.numel()
+            allreduce_gradients(params)        # one flattened NCCL all-reduce of the stage's gradients
         return out, lg
 
     def barrier():

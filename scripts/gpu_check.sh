@@ -3,7 +3,7 @@ set -x
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > gpurun_out/gpu.txt 2>&1
 rm -f gpurun_out/parity_report.txt gpurun_out/summary.txt
-for f in rectifier gate builder tc sccn stage distance; do
+for f in rectifier gate builder tc sccn stage distance graph_and_scale; do
   timeout 900 python -m pytest tests/test_gpu_$f.py -m gpu -q --timeout 800 > gpurun_out/test_$f.log 2>&1
   echo "exit $f: $?" >> gpurun_out/summary.txt
   tail -3 gpurun_out/test_$f.log

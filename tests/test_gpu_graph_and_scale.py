@@ -1,0 +1,93 @@
+"""GPU: CUDA-graph replay equals eager execution; a larger complex (config 3) against the oracle."""
+import copy
+
+import pytest
+import torch
+
+from oracle import glue_oracle as glo
+from oracle import rectifier_oracle as ro
+from tests.helpers import assert_close, assert_fp32_equivalent, hard_concrete_like
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("regime", ["full", "sparse"])
+def test_graphed_step_reproduces_the_eager_step(regime):
+    import topo_audio_autoencoder_b200 as T
+    from topo_audio_autoencoder_b200.graph import GraphedStep
+    n, B, C, L = 12, 4, 64, 3
+    torch.manual_seed(1)
+    kw = dict(gate="binary_gumbel", bias_on="probs") if regime == "full" else dict(gate="hard_concrete", bias_on="logits")
+    stage = T.ComplexStage(n, channels=C, n_layers=L, **kw).cuda().train()
+    N = stage.head.total_simplices
+    g = torch.Generator().manual_seed(3)
+
+    def inputs(seed):
+        gg = torch.Generator().manual_seed(seed)
+        logits = torch.randn(B, N, generator=gg).cuda()
+        if regime == "full":
+            noise = (-torch.empty(2, B, N).exponential_(generator=gg).log()).cuda()
+        else:
+            noise = torch.rand(B, N, generator=gg).clamp_(1e-6, 1 - 1e-6).cuda()
+        return logits, noise
+
+    counts = stage.head._tables.counts
+    ups = [torch.randn(B * c, C, generator=g).cuda() for c in counts] + [torch.ones(B).cuda(), torch.ones(B).cuda()]
+    graphed = GraphedStep(stage, *inputs(10), ups)
+    params = graphed.params
+    for seed in (11, 12):           # new data through the same graph, including different active sets
+        logits, noise = inputs(seed)
+        out_g = {k: v.clone() for k, v in graphed.replay(logits, noise).items()}
+        lg_g = graphed.logits_grad.clone()
+        grads_g = [None if gr is None else gr.clone() for gr in graphed.param_grads]
+        for p in params:
+            p.grad = None
+        le = logits.clone().requires_grad_(True)
+        out_e = stage(le, noise)
+        heads = [out_e[f"rank_{r}"] for r in range(4)] + [out_e["vertex_penalty"], out_e["entropy_loss"]]
+        torch.autograd.backward(heads, ups)
+        live = out_e["complex"].row_off[:, B].tolist()
+        for r in range(4):
+            assert torch.equal(out_g[f"rank_{r}"][:live[r]], out_e[f"rank_{r}"][:live[r]]), f"rank_{r} differs under replay"
+        assert torch.equal(lg_g, le.grad)
+        for p, gg in zip(params, grads_g):
+            if p.grad is None:
+                continue
+            # parameter gradients are accumulated with atomics: equal up to summation order
+            assert_close("graph/param-grad", gg, p.grad, rtol=1e-4, atol=1e-4 * max(1.0, p.grad.abs().max().item()))
+
+
+def test_larger_complex_against_oracle():
+    """Config 3: 24 vertices (12,950 candidate simplices, 10,626 tetrahedra), one SCCN layer, sparse gate."""
+    import topo_audio_autoencoder_b200 as T
+    from oracle import complex_builder_oracle as cbo
+    from oracle.sccn_oracle import OracleSCCN
+    n, C = 24, 64
+    tab = ro.make_tables(n)
+    g = torch.Generator().manual_seed(24)
+    probs = hard_concrete_like((1, sum(tab.sizes)), g, p_zero=0.25, p_one=0.15)
+    torch.manual_seed(5)
+    ref = OracleSCCN(C, 3, 1).train()
+    ours = T.GradientSCCN(C, 3, 1).cuda().train()
+    ours.load_state_dict(ref.state_dict())
+    head = T.ComplexHead(n, embedding_dim=C).cuda()
+    emb = [tuple(t.detach().cpu() for t in (getattr(head, nm)[0].weight, getattr(head, nm)[1].weight, getattr(head, nm)[1].bias))
+           for nm in head._embedding_names]
+    rect_g = T.rectify_batch(probs.cuda(), head.constraints)
+    cx = head.batched_complex(rect_g, sync=True)
+    xs = ours.forward_complex(cx, head.embed(cx))
+
+    parts = torch.split(probs[0], list(tab.sizes))
+    rect = ro.enforce_constraints(*parts, tab)
+    assert torch.equal(rect_g[0].cpu() == 0, torch.cat(rect) == 0)
+    e = glo.active_embeddings(emb, rect)
+    for r, key in enumerate(cbo.RANK_NAMES):
+        got = cx.act_idx[0, head._tables.offsets[r]:head._tables.offsets[r] + cx.rows_max[r]].long().cpu()
+        assert torch.equal(got, e["active_indices"][key]), "active index sets must be bit-exact"
+    adj, inc = cbo.build_sparse_matrices(rect, tab, e["active_indices"])
+    out = ref({f"rank_{r}": e[f"rank_{r}"] for r in range(4)}, inc, adj)
+    ref64 = copy.deepcopy(ref).double()
+    out64 = ref64({f"rank_{r}": e[f"rank_{r}"].double() for r in range(4)},
+                  {k: v.double() for k, v in inc.items()}, {k: v.double() for k, v in adj.items()})
+    for r in range(4):
+        assert_fp32_equivalent(f"large24/rank_{r}", xs[r], out[f"rank_{r}"], out64[f"rank_{r}"])

@@ -21,9 +21,9 @@ def shard_batch(total: int, rank: int, world_size: int) -> Tuple[int, int]:
 
 
 def flatten_grads(params: Iterable[torch.nn.Parameter]) -> Tuple[torch.Tensor, List[torch.nn.Parameter]]:
-    plist = [p for p in params if p.requires_grad]
-    chunks = [(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in plist]
-    return torch.cat(chunks), plist
+    """Parameters that received no gradient (unused on this path: identical on every replica) are skipped."""
+    plist = [p for p in params if p.requires_grad and p.grad is not None]
+    return torch.cat([p.grad.reshape(-1) for p in plist]), plist
 
 
 def allreduce_gradients(params: Iterable[torch.nn.Parameter], average: bool = True) -> None:
@@ -37,8 +37,6 @@ def allreduce_gradients(params: Iterable[torch.nn.Parameter], average: bool = Tr
     offset = 0
     for p in plist:
         n = p.numel()
-        if p.grad is None:
-            p.grad = torch.empty_like(p)
         p.grad.copy_(flat[offset:offset + n].view_as(p))
         offset += n
 

@@ -44,6 +44,8 @@ class GraphedStep:
             out = self._run()
         self.outputs = {k: v for k, v in out.items() if isinstance(v, torch.Tensor)}
         self.logits_grad = self.logits.grad
+        # the graph writes parameter gradients into these static buffers on every replay
+        self.param_grads = [p.grad for p in self.params]
 
     def _run(self):
         for p in self.params:
@@ -61,4 +63,6 @@ class GraphedStep:
         if noise is not None and self.noise is not None:
             self.noise.copy_(noise, non_blocking=True)
         self.graph.replay()
+        for p, g in zip(self.params, self.param_grads):      # re-attach if the caller cleared or replaced .grad
+            p.grad = g
         return self.outputs
