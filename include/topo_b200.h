@@ -237,6 +237,9 @@ typedef struct {
      *   saved_pre[k] = Linear1(m_k) = W1 m_k + b1       (pre-GELU attention hidden layer) */
     float* saved_m[3];
     float* saved_pre[3];
+    /* Optional [3, rows] attention scores Linear2(GELU(pre_k)) (NULL = not used).  Written by
+     * topo_sccn_combine_fwd_tc; required by topo_sccn_combine_bwd_tc, which then evaluates erf once. */
+    float* saved_score;
 } topo_combine_params;
 
 typedef struct {
@@ -278,12 +281,29 @@ int topo_sccn_combine_bwd(const topo_combine_params* p, int64_t rows, const int3
 int topo_sccn_combine_bwd_conv_tc(const topo_combine_params* p, int64_t rows,
                                   const int32_t* n_rows_dev, const topo_combine_grads* g,
                                   const float* workspace, topo_stream_t stream);
+/* The whole combine backward in one tensor-core kernel (channels == 64; needs saved_m, saved_pre and
+ * saved_score from topo_sccn_combine_fwd_tc): LayerNorm / softmax / attention-MLP backward, g_agg, g_x and
+ * all weight-gradient products as bf16x3 tcgen05 GEMMs on operand images staged once and read in both
+ * majors (csrc/combine_bwd_tc.cu).  Same outputs as topo_sccn_combine_bwd; no workspace. */
+int topo_sccn_combine_bwd_tc(const topo_combine_params* p, int64_t rows, const int32_t* n_rows_dev,
+                             const float* grad_out, const topo_combine_grads* g, topo_stream_t stream);
 
 /* Unit-test entry of the tensor-core path (tcgen05.mma kind::tf32, 3xTF32 operand splitting):
  * out[rows, 64] = a[rows, 64] @ w[64, 64].  mode 0: both operands in shared memory (K-major SWIZZLE_128B);
  * mode 3: the A operand in tensor memory (tcgen05.st by the row threads). */
 int topo_debug_gemm_tf32x3(const float* a, const float* w, int64_t rows, int mode, float* out,
                            topo_stream_t stream);
+
+/* Unit-test entry of the bf16x3 tensor-core path (tcgen05.mma kind::f16 on three bf16 parts per fp32
+ * operand, six part products, fp32 accumulation; csrc/tc16.cuh).  One 16-bit SWIZZLE_128B image serves
+ * both operand majors:
+ *   mode 0: out[rows, 64] = a @ w     (w stored [in][out], read MN-major)
+ *   mode 1: out[rows, 64] = a @ w^T   (w stored [out][in], read K-major)
+ *   mode 2: out[64, 64]  += a^T w     (w is a second [rows, 64] matrix; both read MN-major, contraction over rows)
+ * mn_lbo / mn_sbo / mn_kstep: descriptor fields of the MN-major operands in bytes (16384 / 1024 / 2048 for
+ * the layouts in tc16.cuh; exposed so the test can pin them). */
+int topo_debug_gemm_bf16x3(const float* a, const float* w, int64_t rows, int mode, int mn_lbo, int mn_sbo,
+                           int mn_kstep, float* out, topo_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * D1-D3. Tiled pairwise spectral distance.  Replaces the pair loop of compute_distances

@@ -1,0 +1,53 @@
+"""GPU: pin the MN-major descriptor fields of the bf16x3 path by trying candidates against fp64."""
+import itertools
+import sys
+
+import torch
+
+sys.path.insert(0, ".")
+from topo_audio_autoencoder_b200._lib import lib, ptr, stream  # noqa: E402
+
+
+def err(out, want, cond):
+    if not torch.isfinite(out).all():
+        return float("inf")
+    return ((out.double() - want).abs() / cond).max().item()
+
+
+def main():
+    g = torch.Generator().manual_seed(3)
+    rows = 300
+    a = (torch.randn(rows, 64, generator=g) * torch.logspace(-2, 2, 64)).cuda()
+    w = torch.randn(64, 64, generator=g).cuda()
+    b = torch.randn(rows, 64, generator=g).cuda()
+
+    def run(mode, second, lbo, sbo, kstep, shape):
+        out = torch.zeros(*shape, device="cuda")
+        rc = lib.topo_debug_gemm_bf16x3(ptr(a), ptr(second), rows, mode, lbo, sbo, kstep, ptr(out), stream())
+        try:
+            torch.cuda.synchronize()
+        except Exception as e:  # noqa: BLE001
+            print("CUDA fault", mode, lbo, sbo, kstep, e)
+            raise
+        return rc, out
+
+    # mode 1: K-major both (baseline for the bf16 path)
+    rc, out = run(1, w, 16384, 1024, 2048, (rows, 64))
+    want = a.double() @ w.double().t()
+    cond = a.double().abs() @ w.double().abs().t()
+    print(f"mode 1 (K-major x K-major): rc={rc} err={err(out, want, cond):.3e}", flush=True)
+
+    want0 = a.double() @ w.double()
+    cond0 = a.double().abs() @ w.double().abs()
+    want2 = a.double().t() @ b.double()
+    cond2 = a.double().abs().t() @ b.double().abs()
+    for lbo, sbo, kstep in itertools.product((16384, 8192, 0, 1024, 128), (1024, 2048, 128, 8192), (2048, 1024, 4096, 256)):
+        _, o0 = run(0, w, lbo, sbo, kstep, (rows, 64))
+        _, o2 = run(2, b, lbo, sbo, kstep, (64, 64))
+        e0, e2 = err(o0, want0, cond0), err(o2, want2, cond2)
+        flag = " <== OK" if (e0 < 2e-6 and e2 < 2e-6) else ""
+        print(f"lbo={lbo:6d} sbo={sbo:5d} kstep={kstep:5d}: mode0 err={e0:.3e}  mode2 err={e2:.3e}{flag}", flush=True)
+
+
+if __name__ == "__main__":
+    main()

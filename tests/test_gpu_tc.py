@@ -121,3 +121,120 @@ def test_tensor_core_conv_backward_matches_the_fp32_kernel(n_msgs, rows):
             report(f"tc/conv-bwd/{name}/msgs={n_msgs}/rows={rows}/k={k}", tcv.float(), want.float())
             assert err < 2e-6, (name, k, err)
         assert (results[1][0][k][live_n:] == 0).all()
+
+
+@pytest.mark.parametrize("mode,shape", [(0, None), (1, None), (2, (64, 64))])
+@pytest.mark.parametrize("rows", [1, 128, 300, 20000])
+def test_bf16x3_gemm_in_both_operand_majors(mode, shape, rows):
+    """One 16-bit SWIZZLE_128B image read K-major (mode 1) and MN-major (modes 0, 2: y = x W with W stored
+    [in][out], and the row contraction x^T y) -- the descriptor fields pinned here are the ones tc16.cuh uses."""
+    from topo_audio_autoencoder_b200._lib import lib, check, ptr, stream
+    g = torch.Generator().manual_seed(rows + mode)
+    a = (torch.randn(rows, 64, generator=g) * torch.logspace(-3, 3, 64)).cuda()
+    second = (torch.randn(rows, 64, generator=g) if mode == 2 else torch.randn(64, 64, generator=g)).cuda()
+    out = torch.zeros(*(shape or (rows, 64)), device="cuda")
+    check(lib.topo_debug_gemm_bf16x3(ptr(a), ptr(second), rows, mode, 16384, 1024, 2048, ptr(out), stream()))
+    torch.cuda.synchronize()
+    a64, s64 = a.double(), second.double()
+    if mode == 0:
+        want, cond = a64 @ s64, a64.abs() @ s64.abs()
+    elif mode == 1:
+        want, cond = a64 @ s64.t(), a64.abs() @ s64.abs().t()
+    else:
+        want, cond = a64.t() @ s64, a64.abs().t() @ s64.abs()
+    err = ((out.double() - want).abs() / cond).max().item()
+    report(f"tc/gemm-bf16x3/mode={mode}/rows={rows}", out, want.float())
+    assert torch.isfinite(out).all()
+    assert err < 5e-7, f"relative-to-condition error {err:.3e}"
+
+
+@pytest.mark.parametrize("n_msgs,apply_ln,rows,residual", [(3, True, 1000, True), (2, False, 130, True), (1, True, 64, False),
+                                                            (2, True, 40000, True), (3, False, 5000, True)])
+def test_fused_tensor_core_backward_matches_fp64_autograd(n_msgs, apply_ln, rows, residual):
+    """topo_sccn_combine_bwd_tc (one bf16x3 kernel) against fp64 autograd of the same formula, with the FFMA +
+    3xTF32 two-kernel backward as the accuracy yardstick."""
+    import ctypes as C
+    from topo_audio_autoencoder_b200._lib import lib, check, ptr, stream, CombineGrads
+    from topo_audio_autoencoder_b200.custom_sccn import _make_params
+    g = torch.Generator().manual_seed(rows * 3 + n_msgs)
+    ch = 64
+    rnd = lambda *s: torch.randn(*s, generator=g).cuda()     # noqa: E731
+    aggs = [rnd(rows, ch) * 1.5 for _ in range(n_msgs)]
+    ws = [rnd(ch, ch) * 0.2 for _ in range(n_msgs)]
+    scales = [torch.tensor([0.7 + 0.2 * k]).cuda() for k in range(n_msgs)]
+    x = rnd(rows, ch) if residual else None
+    tensors = [rnd(ch, ch) * 0.2, rnd(ch) * 0.1, rnd(ch) * 0.3, rnd(1), 1 + 0.1 * rnd(ch), 0.1 * rnd(ch)]
+    g_out = rnd(rows, ch)
+    live_n = rows - 3 if rows > 100 else rows
+    live = torch.tensor([live_n], dtype=torch.int32).cuda()
+    saved = ([torch.zeros(rows, ch, device="cuda") for _ in range(n_msgs)],
+             [torch.zeros(rows, ch, device="cuda") for _ in range(n_msgs)], torch.zeros(3, rows, device="cuda"))
+    params = _make_params(ch, n_msgs, aggs, ws, scales, x, tensors, 1e-5, apply_ln, saved)
+    out = torch.zeros(rows, ch, device="cuda")
+    check(lib.topo_sccn_combine_fwd_tc(C.byref(params), rows, ptr(live, torch.int32), ptr(out), stream()))
+
+    def run(fused):
+        res = {"g_agg": [torch.zeros(rows, ch, device="cuda") for _ in range(n_msgs)],
+               "wprod": [torch.zeros(ch, ch, device="cuda") for _ in range(n_msgs)],
+               "g_x": torch.zeros(rows, ch, device="cuda") if residual else None,
+               "w1": torch.zeros(ch, ch, device="cuda"), "b1": torch.zeros(ch, device="cuda"),
+               "w2": torch.zeros(ch, device="cuda"), "b2": torch.zeros(1, device="cuda"),
+               "gamma": torch.zeros(ch, device="cuda"), "beta": torch.zeros(ch, device="cuda")}
+        grads = CombineGrads()
+        for k in range(n_msgs):
+            grads.g_agg[k], grads.g_wprod[k] = ptr(res["g_agg"][k]), ptr(res["wprod"][k])
+        grads.g_x = ptr(res["g_x"])
+        grads.g_att_w1, grads.g_att_b1, grads.g_att_w2, grads.g_att_b2 = ptr(res["w1"]), ptr(res["b1"]), ptr(res["w2"]), ptr(res["b2"])
+        grads.g_ln_gamma, grads.g_ln_beta = ptr(res["gamma"]), ptr(res["beta"])
+        if fused:
+            check(lib.topo_sccn_combine_bwd_tc(C.byref(params), rows, ptr(live, torch.int32), ptr(g_out), C.byref(grads), stream()))
+        else:
+            ws_buf = torch.zeros(n_msgs * rows * ch, device="cuda")
+            check(lib.topo_sccn_combine_bwd_attention(C.byref(params), rows, ptr(live, torch.int32), ptr(g_out), C.byref(grads),
+                                                      ptr(ws_buf), stream()))
+            check(lib.topo_sccn_combine_bwd_conv_tc(C.byref(params), rows, ptr(live, torch.int32), C.byref(grads), ptr(ws_buf), stream()))
+        torch.cuda.synchronize()
+        return res
+
+    fused, two_kernel = run(True), run(False)
+
+    # fp64 autograd of the same formula on the live rows
+    leaf = lambda t: t[:live_n].double().clone().requires_grad_(True) if t.dim() == 2 and t.shape[0] == rows else t.double().clone().requires_grad_(True)  # noqa: E731
+    a64 = [leaf(a) for a in aggs]
+    w64 = [w.double().clone().requires_grad_(True) for w in ws]
+    x64 = leaf(x) if residual else None
+    w1, b1, w2, b2, gam, bet = (t.double().clone().requires_grad_(True) for t in tensors)
+    prods = [a @ w for a, w in zip(a64, w64)]
+    for p_ in prods:
+        p_.retain_grad()
+    m = [s.double() * p_ + (x64 if residual else 0) for p_, s in zip(prods, scales)]
+    sc = torch.stack([torch.nn.functional.gelu(mk @ w1.t() + b1) @ w2 + b2 for mk in m])
+    att = torch.softmax(sc, dim=0)
+    y = sum(att[k].unsqueeze(1) * m[k] for k in range(n_msgs))
+    if apply_ln:
+        y = torch.nn.functional.layer_norm(y, (ch,), gam, bet, 1e-5)
+    y.backward(g_out[:live_n].double())
+
+    def check_one(name, got_f, got_2, want):
+        scale = want.abs().max().item() + 1e-30
+        e_f = (got_f.double() - want).abs().max().item() / scale
+        e_2 = (got_2.double() - want).abs().max().item() / scale
+        report(f"tc/bwd-fused/{name}/msgs={n_msgs}/ln={apply_ln}/rows={rows}", got_f.float(), want.float())
+        assert torch.isfinite(got_f).all(), name
+        assert e_f <= 4 * e_2 + 2e-6, f"{name}: fused {e_f:.3e} vs two-kernel {e_2:.3e} (relative to max |want|, both against fp64)"
+
+    for k in range(n_msgs):
+        check_one(f"g_agg{k}", fused["g_agg"][k][:live_n], two_kernel["g_agg"][k][:live_n], a64[k].grad)
+        # g_wprod[k] = agg_k^T dL/dm_k  =  d/d(agg_k W_k) scaled back by 1 / scale_k
+        want_p = a64[k].detach().t() @ (prods[k].grad / scales[k].double())
+        check_one(f"wprod{k}", fused["wprod"][k], two_kernel["wprod"][k], want_p)
+        assert (fused["g_agg"][k][live_n:] == 0).all()
+    if residual:
+        check_one("g_x", fused["g_x"][:live_n], two_kernel["g_x"][:live_n], x64.grad)
+    check_one("w1", fused["w1"], two_kernel["w1"], w1.grad)
+    check_one("b1", fused["b1"], two_kernel["b1"], b1.grad)
+    check_one("w2", fused["w2"], two_kernel["w2"], w2.grad)
+    check_one("b2", fused["b2"], two_kernel["b2"], b2.grad)
+    if apply_ln:
+        check_one("gamma", fused["gamma"], two_kernel["gamma"], gam.grad)
+        check_one("beta", fused["beta"], two_kernel["beta"], bet.grad)

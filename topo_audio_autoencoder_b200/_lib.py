@@ -35,7 +35,7 @@ class CombineParams(C.Structure):
                 ("att_w2", C.c_void_p), ("att_b2", C.c_void_p),
                 ("ln_gamma", C.c_void_p), ("ln_beta", C.c_void_p),
                 ("ln_eps", C.c_float), ("apply_ln", C.c_int),
-                ("saved_m", C.c_void_p * 3), ("saved_pre", C.c_void_p * 3)]
+                ("saved_m", C.c_void_p * 3), ("saved_pre", C.c_void_p * 3), ("saved_score", C.c_void_p)]
 
 
 class CombineGrads(C.Structure):
@@ -86,7 +86,9 @@ SIGNATURES = {
     "topo_sccn_combine_bwd_attention": [C.POINTER(CombineParams), _I64, _P, _P, C.POINTER(CombineGrads), _P, _P],
     "topo_sccn_combine_bwd_conv": [C.POINTER(CombineParams), _I64, _P, C.POINTER(CombineGrads), _P, _P],
     "topo_sccn_combine_bwd_conv_tc": [C.POINTER(CombineParams), _I64, _P, C.POINTER(CombineGrads), _P, _P],
+    "topo_sccn_combine_bwd_tc": [C.POINTER(CombineParams), _I64, _P, _P, C.POINTER(CombineGrads), _P],
     "topo_debug_gemm_tf32x3": [_P, _P, _I64, _I32, _P, _P],
+    "topo_debug_gemm_bf16x3": [_P, _P, _I64, _I32, _I32, _I32, _I32, _P, _P],
     "topo_distance_padded_size": [C.POINTER(_I64), _I32],
     "topo_distance_prepare": [_P, _I64, _I64, C.POINTER(_I64), _I32, _F, _P, _P, _P, _P],
     "topo_distance_rows": [_P, _P, _P, _I64, C.POINTER(_I64), _I32, _I64, _I64, _I64, _I64, _P, _P],
@@ -116,8 +118,8 @@ KERNELS_PER_CALL = {
     "topo_embed_bwd": 2, "topo_layernorm_fwd": 1, "topo_layernorm_bwd": 1, "topo_operators_count": 2,
     "topo_operators_fill": 1, "topo_operators_bwd": 1, "topo_sccn_aggregate_fwd": 2, "topo_sccn_aggregate_bwd": 2,
     "topo_spmm_csr": 1, "topo_sddmm_csr": 1, "topo_sccn_combine_fwd": 1, "topo_sccn_combine_fwd_tc": 1, "topo_sccn_combine_bwd": 2,
-    "topo_sccn_combine_bwd_attention": 1, "topo_sccn_combine_bwd_conv": 1, "topo_sccn_combine_bwd_conv_tc": 1, "topo_distance_prepare": 1,
-    "topo_distance_rows": 1, "topo_debug_gemm_tf32x3": 1,
+    "topo_sccn_combine_bwd_attention": 1, "topo_sccn_combine_bwd_conv": 1, "topo_sccn_combine_bwd_conv_tc": 1, "topo_sccn_combine_bwd_tc": 1, "topo_distance_prepare": 1,
+    "topo_distance_rows": 1, "topo_debug_gemm_tf32x3": 1, "topo_debug_gemm_bf16x3": 1,
 }
 
 

@@ -345,6 +345,7 @@ __global__ void __launch_bounds__(128 * NQ, 1) combine_fwd_tc_kernel(topo_combin
 #pragma unroll
             for (int g = 0; g < NQ; ++g) score += red[g * kTileRows + r];
             if (k == 0) sc0 = score; else if (k == 1) sc1 = score; else sc2 = score;
+            if (P.saved_score != nullptr && h == 0 && row < live) P.saved_score[k * rows + row] = score;
         }
         // softmax over the messages, mix straight from tensor memory
         float mx = sc0;

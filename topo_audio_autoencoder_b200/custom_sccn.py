@@ -92,6 +92,9 @@ COMBINE_IMPL = "tc"
 # keep m_k and the pre-GELU attention layer from the forward (2 x n_msgs x rows x C floats per call) so the
 # backward does not recompute two of its five GEMMs per message
 SAVE_ACTIVATIONS = True
+# with the tensor-core forward's saved activations, run the whole combine backward as ONE bf16x3 tensor-core
+# kernel (csrc/combine_bwd_tc.cu) instead of the FFMA attention kernel + the 3xTF32 conv kernel
+FUSED_BACKWARD = True
 
 
 class _CombineFn(torch.autograd.Function):
@@ -111,21 +114,23 @@ class _CombineFn(torch.autograd.Function):
         if SAVE_ACTIVATIONS and any(ctx.needs_input_grad):
             # the messages and the pre-GELU attention layer, kept for the backward (skips both recompute GEMMs)
             saved = ([torch.empty(rows, ch, dtype=torch.float32, device=dev) for _ in range(n_msgs)],
-                     [torch.empty(rows, ch, dtype=torch.float32, device=dev) for _ in range(n_msgs)])
+                     [torch.empty(rows, ch, dtype=torch.float32, device=dev) for _ in range(n_msgs)],
+                     torch.empty(3, rows, dtype=torch.float32, device=dev))      # attention scores (tensor-core forward)
         params = _make_params(ch, n_msgs, aggs, ws, scales, x_c, tensors, ln_eps, apply_ln, saved)
         # rows past the live count are never read by any kernel; they are zero-filled only where the tensor is
         # handed to the caller (last layer), so that padded buffers are safe to reduce over
         out = (torch.zeros if zero_dead_rows else torch.empty)(rows, ch, dtype=torch.float32, device=dev)
-        fwd = lib.topo_sccn_combine_fwd_tc if (COMBINE_IMPL == "tc" and ch == 64) else lib.topo_sccn_combine_fwd
+        use_tc = COMBINE_IMPL == "tc" and ch == 64
+        fwd = lib.topo_sccn_combine_fwd_tc if use_tc else lib.topo_sccn_combine_fwd
         check(fwd(C.byref(params), rows, ptr(n_rows_dev, torch.int32), ptr(out), stream()))
         ctx.save_for_backward(x_c, n_rows_dev, *tensors, *aggs, *ws, *scales)
         ctx.saved_act = saved
-        ctx.cfg = (n_msgs, bool(apply_ln), float(ln_eps), x is not None)
+        ctx.cfg = (n_msgs, bool(apply_ln), float(ln_eps), x is not None, use_tc and saved is not None)
         return out
 
     @staticmethod
     def backward(ctx, g_out):
-        n_msgs, apply_ln, ln_eps, has_x = ctx.cfg
+        n_msgs, apply_ln, ln_eps, has_x, fused = ctx.cfg
         saved = ctx.saved_tensors
         x_c, n_rows_dev, tensors = saved[0], saved[1], list(saved[2:8])
         aggs = list(saved[8:8 + n_msgs])
@@ -148,12 +153,17 @@ class _CombineFn(torch.autograd.Function):
         grads.g_att_w1, grads.g_att_b1 = ptr(g_w1), ptr(g_b1)
         grads.g_att_w2, grads.g_att_b2 = ptr(g_w2), ptr(g_b2)
         grads.g_ln_gamma, grads.g_ln_beta = ptr(g_g), ptr(g_b)
-        workspace = torch.empty(n_msgs * rows * ch, dtype=torch.float32, device=dev)
         g_out = g_out.contiguous()     # named: a temporary would be freed before the launch reads it
-        check(lib.topo_sccn_combine_bwd_attention(C.byref(params), rows, ptr(n_rows_dev, torch.int32),
-                                                  ptr(g_out), C.byref(grads), ptr(workspace), stream()))
-        conv = lib.topo_sccn_combine_bwd_conv_tc if (COMBINE_IMPL == "tc" and ch == 64) else lib.topo_sccn_combine_bwd_conv
-        check(conv(C.byref(params), rows, ptr(n_rows_dev, torch.int32), C.byref(grads), ptr(workspace), stream()))
+        if fused and FUSED_BACKWARD:
+            # one tensor-core kernel: attention / LayerNorm backward, input gradients and weight-gradient products
+            check(lib.topo_sccn_combine_bwd_tc(C.byref(params), rows, ptr(n_rows_dev, torch.int32), ptr(g_out),
+                                               C.byref(grads), stream()))
+        else:
+            workspace = torch.empty(n_msgs * rows * ch, dtype=torch.float32, device=dev)
+            check(lib.topo_sccn_combine_bwd_attention(C.byref(params), rows, ptr(n_rows_dev, torch.int32),
+                                                      ptr(g_out), C.byref(grads), ptr(workspace), stream()))
+            conv = lib.topo_sccn_combine_bwd_conv_tc if (COMBINE_IMPL == "tc" and ch == 64) else lib.topo_sccn_combine_bwd_conv
+            check(conv(C.byref(params), rows, ptr(n_rows_dev, torch.int32), C.byref(grads), ptr(workspace), stream()))
         # finish the conv-weight chain: dW_k = scale_k P_k,  dscale_k = <W_k, P_k>
         g_ws = [wprod[k] * scales[k] for k in range(n_msgs)]
         g_ss = [(wprod[k] * ws[k]).sum().reshape(scales[k].shape) for k in range(n_msgs)]
@@ -170,6 +180,7 @@ def _make_params(ch, n_msgs, aggs, ws, scales, x, tensors, ln_eps, apply_ln, sav
         p.scale[k] = ptr(scales[k]) if k < n_msgs else None
         p.saved_m[k] = ptr(saved[0][k]) if (saved is not None and k < n_msgs) else None
         p.saved_pre[k] = ptr(saved[1][k]) if (saved is not None and k < n_msgs) else None
+    p.saved_score = ptr(saved[2]) if (saved is not None and len(saved) > 2) else None
     p.x = ptr(x)
     p.att_w1, p.att_b1, p.att_w2, p.att_b2 = (ptr(t) for t in tensors[:4])
     p.ln_gamma, p.ln_beta = ptr(tensors[4]), ptr(tensors[5])
