@@ -38,14 +38,17 @@ constexpr uint32_t kWPart = kC * 128;                     // 8 KB
 constexpr uint32_t kWImg = 3 * kWPart;                    // 24 KB
 
 struct BwdSmem {
-    static constexpr uint32_t kQ = 0;                     // Q then P: the M = 128 over-read of Q lands in P, of P in W1
+    static constexpr uint32_t kQ = 0;
     static constexpr uint32_t kP = kImg;
     static constexpr uint32_t kW1 = 2 * kImg;
     static constexpr uint32_t kWk = kW1 + kWImg;          // 3 conv weights
-    static constexpr uint32_t kVec = kWk + 3 * kWImg;     // w2[64], gamma[64]
-    static constexpr uint32_t kRed = kVec + 2 * kC * 4;   // [7 slots][4 column groups][128 rows]: mean, var, c1, c2, da_0..2
-    static constexpr uint32_t kTotal = kRed + 7 * 4 * kTileRows * 4;
+    static constexpr uint32_t kDy = kWk + 3 * kWImg;      // dy tile [128][64] fp32, 16-byte chunks XOR-swizzled by row
+    static constexpr uint32_t kVec = kDy + kTileRows * kC * 4;   // w2[64], gamma[64]
+    static constexpr uint32_t kAtt = kVec + 2 * kC * 4;   // softmax weights [3][128]
+    static constexpr uint32_t kBar = kAtt + 3 * kTileRows * 4;   // mbarrier, tensor-memory base
+    static constexpr uint32_t kTotal = kBar + 16;
 };
+static_assert(BwdSmem::kTotal <= 232448, "shared-memory budget of one CTA");
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
     uint32_t r[16];
@@ -60,52 +63,27 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-__device__ __forceinline__ void load_slice(const float* __restrict__ src, long long row, int col0, bool ok, float (&v)[16]) {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (ok) t = __ldg(reinterpret_cast<const float4*>(src + row * kC + col0) + j);
-        v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
+// eight consecutive columns of one row (two 128-bit loads; eight lanes cover a whole 256-byte row)
+__device__ __forceinline__ void load_chunk(const float* __restrict__ src, long long row, int chunk, bool ok, float (&v)[8]) {
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    if (ok) {
+        const float4* p = reinterpret_cast<const float4*>(src + row * kC) + chunk * 2;
+        a = __ldg(p);
+        b = __ldg(p + 1);
     }
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
 }
 
-__device__ __forceinline__ void store_slice_image(uint8_t* img, int r, int q, const float (&v)[16]) {
-    float lo[8], hi[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        lo[i] = v[i];
-        hi[i] = v[8 + i];
-    }
-    store_split8(img, kPart, r, 2 * q, lo);
-    store_split8(img, kPart, r, 2 * q + 1, hi);
+// sum over the eight lanes that share a tile row
+__device__ __forceinline__ float row_sum8(float v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    return v;
 }
 
-// Sum over the warp's 32 lanes of each of 16 per-lane values; lane l returns column (l >> 1) & 15.
-__device__ __forceinline__ float colsum16(const float (&v)[16], int lane) {
-    float a[8], c[4], d[2];
-    bool up = lane & 16;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const float send = up ? v[i] : v[i + 8], keep = up ? v[i + 8] : v[i];
-        a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-    }
-    up = lane & 8;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const float send = up ? a[i] : a[i + 4], keep = up ? a[i + 4] : a[i];
-        c[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-    }
-    up = lane & 4;
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        const float send = up ? c[i] : c[i + 2], keep = up ? c[i + 2] : c[i];
-        d[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-    }
-    up = lane & 2;
-    const float send = up ? d[0] : d[1], keep = up ? d[1] : d[0];
-    float e = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-    e += __shfl_xor_sync(0xffffffffu, e, 1);
-    return e;
+__device__ __forceinline__ uint32_t dy_off(int row, int c16 /* 0..15 */) {
+    return static_cast<uint32_t>(row * 256 + ((c16 ^ (row & 7)) << 4));
 }
 
 __device__ __forceinline__ void stage_weight16(const float* __restrict__ w, uint8_t* img, int tid) {
@@ -118,6 +96,12 @@ __device__ __forceinline__ void stage_weight16(const float* __restrict__ w, uint
     }
 }
 
+// Two thread <-> data mappings:
+//   chunk map: thread t owns columns [8 c, 8 c + 8), c = t % 8, of tile rows t / 8 and t / 8 + 64.  Global
+//              loads are coalesced (eight lanes = one 256-byte row), row reductions are three shuffles, and
+//              the column sums accumulate in registers.  All element-wise work runs in this mapping.
+//   row map:   thread (q, r) = (t / 128, t % 128) owns columns [16 q, 16 q + 16) of row r = TMEM lane r.  Only
+//              the two tensor-memory epilogues use it; dy and the softmax weights cross over in shared memory.
 __global__ void __launch_bounds__(kThreads, 1) combine_bwd_fused_kernel(topo_combine_params P, long long rows,
                                                                         const int* __restrict__ n_rows_dev,
                                                                         const float* __restrict__ grad_out,
@@ -126,36 +110,38 @@ __global__ void __launch_bounds__(kThreads, 1) combine_bwd_fused_kernel(topo_com
     uint8_t* base = smem_raw;
     uint8_t* q_img = base + BwdSmem::kQ;
     uint8_t* p_img = base + BwdSmem::kP;
+    uint8_t* dy_s = base + BwdSmem::kDy;
     float* vecs = reinterpret_cast<float*>(base + BwdSmem::kVec);
-    float* red = reinterpret_cast<float*>(base + BwdSmem::kRed);
-    __shared__ uint64_t bar;
-    __shared__ uint32_t tmem_base_smem;
+    float* att_s = reinterpret_cast<float*>(base + BwdSmem::kAtt);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(base + BwdSmem::kBar);
+    uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(base + BwdSmem::kBar + 8);
 
     const long long live = n_rows_dev ? min(static_cast<long long>(*n_rows_dev), rows) : rows;
     const long long tiles = (live + kTileRows - 1) / kTileRows;
     if (blockIdx.x >= tiles) return;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int q = tid >> 7, r = tid & 127, col0 = q * kCW;
+    const int q = tid >> 7, r = tid & 127, col0 = q * kCW;     // row map
+    const int c = tid & 7, ra = tid >> 3;                       // chunk map: rows ra and ra + 64
     const int n_msgs = P.n_msgs;
     const bool apply_ln = P.apply_ln != 0;
 
     if (tid == 0) {
-        mbar_init(&bar, 1);
+        mbar_init(bar, 1);
         fence_barrier_init();
     }
-    if (warp == 0) tmem_alloc(&tmem_base_smem, 512);
+    if (warp == 0) tmem_alloc(tmem_base_smem, 512);
     stage_weight16(P.att_w1, base + BwdSmem::kW1, tid);
     for (int k = 0; k < n_msgs; ++k) stage_weight16(P.w[k], base + BwdSmem::kWk + k * kWImg, tid);
-    for (int c = tid; c < kC; c += kThreads) {
-        vecs[c] = __ldg(P.att_w2 + c);
-        vecs[kC + c] = apply_ln ? __ldg(P.ln_gamma + c) : 1.f;
+    for (int i = tid; i < kC; i += kThreads) {
+        vecs[i] = __ldg(P.att_w2 + i);
+        vecs[kC + i] = apply_ln ? __ldg(P.ln_gamma + i) : 1.f;
     }
     fence_async_shared();
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
-    const uint32_t tmem_base = tmem_base_smem;
+    const uint32_t tmem_base = *tmem_base_smem;
     // tensor-memory columns: T | Ga | DW1 | DWp_0 | DWp_1 | DWp_2
     const uint32_t tm_t = tmem_base, tm_ga = tmem_base + 64, tm_dw1 = tmem_base + 128, tm_dwp = tmem_base + 192;
     const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
@@ -164,226 +150,287 @@ __global__ void __launch_bounds__(kThreads, 1) combine_bwd_fused_kernel(topo_com
     float scale_r[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) scale_r[k] = k < n_msgs ? __ldg(P.scale[k]) : 0.f;
+    const float* w2c = vecs + 8 * c;                            // this thread's eight columns of w2 and gamma
+    const float* gmc = vecs + kC + 8 * c;
 
     uint32_t parity = 0, tiles_done = 0;
-    float p_b1 = 0.f, p_w2 = 0.f, p_gamma = 0.f, p_beta = 0.f, p_b2 = 0.f;
-    float w2r[kCW];
+    float p_b1[8], p_w2[8], p_gamma[8], p_beta[8], p_b2 = 0.f;  // column sums over this thread's rows
 #pragma unroll
-    for (int j = 0; j < kCW; ++j) w2r[j] = vecs[col0 + j];
+    for (int i = 0; i < 8; ++i) p_b1[i] = p_w2[i] = p_gamma[i] = p_beta[i] = 0.f;
 
     for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++tiles_done) {
-        const long long row = tile * kTileRows + r;
-        const bool alive = row < live;
-        // ---------------- phase A: attention weights, LayerNorm backward, dscore ----------------
-        float dy[kCW];
-        load_slice(grad_out, row, col0, alive, dy);
-        float sc[3], att[3], dsc[3];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) sc[k] = (k < n_msgs && alive) ? __ldg(P.saved_score + k * rows + row) : 0.f;
+        const long long row0 = tile * kTileRows;
+        const long long grow[2] = {row0 + ra, row0 + ra + 64};
+        const bool alive[2] = {grow[0] < live, grow[1] < live};
+        // ---------------- phase A (chunk map): softmax weights, LayerNorm backward, dscore ----------------
+        float dy[2][8], dsc[2][3];
         {
-            float mx = sc[0];
-            if (n_msgs > 1) mx = fmaxf(mx, sc[1]);
-            if (n_msgs > 2) mx = fmaxf(mx, sc[2]);
-            const float e0 = expf(sc[0] - mx), e1 = n_msgs > 1 ? expf(sc[1] - mx) : 0.f, e2 = n_msgs > 2 ? expf(sc[2] - mx) : 0.f;
-            const float es = e0 + e1 + e2;
-            att[0] = e0 / es; att[1] = e1 / es; att[2] = e2 / es;
-        }
-        if (apply_ln) {
-            float y[kCW];
+            float mk[3][2][8], att[2][3];
 #pragma unroll
-            for (int j = 0; j < kCW; ++j) y[j] = 0.f;
-#pragma unroll 1
-            for (int k = 0; k < n_msgs; ++k) {
-                float mk[kCW];
-                load_slice(P.saved_m[k], row, col0, alive, mk);
-                const float a = k == 0 ? att[0] : (k == 1 ? att[1] : att[2]);
+            for (int j = 0; j < 2; ++j) {
+                load_chunk(grad_out, grow[j], c, alive[j], dy[j]);
 #pragma unroll
-                for (int j = 0; j < kCW; ++j) y[j] = fmaf(a, mk[j], y[j]);
-            }
-            float part = 0.f;
-#pragma unroll
-            for (int j = 0; j < kCW; ++j) part += y[j];
-            red[(0 * 4 + q) * kTileRows + r] = part;
-            __syncthreads();
-            const float mean = (red[0 * kTileRows + r] + red[1 * kTileRows + r] + red[2 * kTileRows + r] + red[3 * kTileRows + r]) * (1.0f / kC);
-            float var = 0.f;
-#pragma unroll
-            for (int j = 0; j < kCW; ++j) var = fmaf(y[j] - mean, y[j] - mean, var);
-            red[(1 * 4 + q) * kTileRows + r] = var;
-            __syncthreads();
-            const float* rv = red + 4 * kTileRows;
-            const float rstd = 1.0f / sqrtf((rv[r] + rv[kTileRows + r] + rv[2 * kTileRows + r] + rv[3 * kTileRows + r]) * (1.0f / kC) + P.ln_eps);
-            float gx[kCW], c1 = 0.f, c2 = 0.f;
-#pragma unroll
-            for (int j = 0; j < kCW; ++j) {
-                y[j] = (y[j] - mean) * rstd;                       // x-hat
-                gx[j] = dy[j] * y[j];                              // gamma gradient term
-                const float gy = dy[j] * vecs[kC + col0 + j];
-                c1 += gy;
-                c2 = fmaf(gy, y[j], c2);
-            }
-            p_gamma += colsum16(gx, lane);
-            p_beta += colsum16(dy, lane);
-            red[(2 * 4 + q) * kTileRows + r] = c1;
-            red[(3 * 4 + q) * kTileRows + r] = c2;
-            __syncthreads();
-            const float* r1 = red + 8 * kTileRows;
-            const float* r2 = red + 12 * kTileRows;
-            c1 = (r1[r] + r1[kTileRows + r] + r1[2 * kTileRows + r] + r1[3 * kTileRows + r]) * (1.0f / kC);
-            c2 = (r2[r] + r2[kTileRows + r] + r2[2 * kTileRows + r] + r2[3 * kTileRows + r]) * (1.0f / kC);
-#pragma unroll
-            for (int j = 0; j < kCW; ++j) dy[j] = rstd * (dy[j] * vecs[kC + col0 + j] - c1 - y[j] * c2);
-        }
-        // dscore_k = a_k (dy . m_k - sum_j a_j dy . m_j)
-#pragma unroll 1
-        for (int k = 0; k < n_msgs; ++k) {
-            float mk[kCW];
-            load_slice(P.saved_m[k], row, col0, alive, mk);
-            float part = 0.f;
-#pragma unroll
-            for (int j = 0; j < kCW; ++j) part = fmaf(dy[j], mk[j], part);
-            red[((4 + k) * 4 + q) * kTileRows + r] = part;     // own slots: c1 / c2 may still be being read
-        }
-        __syncthreads();
-        {
-            float da[3], dot = 0.f;
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                const float* rk = red + (4 + k) * 4 * kTileRows;
-                da[k] = k < n_msgs ? (rk[r] + rk[kTileRows + r] + rk[2 * kTileRows + r] + rk[3 * kTileRows + r]) : 0.f;
-                dot = fmaf(att[k], da[k], dot);
+                for (int k = 0; k < 3; ++k)
+                    if (k < n_msgs) load_chunk(P.saved_m[k], grow[j], c, alive[j], mk[k][j]);
             }
 #pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                dsc[k] = (k < n_msgs && alive) ? att[k] * (da[k] - dot) : 0.f;
-                if (q == 0) p_b2 += dsc[k];
+            for (int j = 0; j < 2; ++j) {
+                float sc[3];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) sc[k] = (k < n_msgs && alive[j]) ? __ldg(P.saved_score + k * rows + grow[j]) : 0.f;
+                float mx = sc[0];
+                if (n_msgs > 1) mx = fmaxf(mx, sc[1]);
+                if (n_msgs > 2) mx = fmaxf(mx, sc[2]);
+                const float e0 = expf(sc[0] - mx), e1 = n_msgs > 1 ? expf(sc[1] - mx) : 0.f, e2 = n_msgs > 2 ? expf(sc[2] - mx) : 0.f;
+                const float es = e0 + e1 + e2;
+                att[j][0] = e0 / es; att[j][1] = e1 / es; att[j][2] = e2 / es;
+                if (c == 0) {
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) att_s[k * kTileRows + ra + 64 * j] = att[j][k];
+                }
+                if (apply_ln) {
+                    float y[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) y[i] = 0.f;
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        if (k < n_msgs) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) y[i] = fmaf(att[j][k], mk[k][j][i], y[i]);
+                        }
+                    }
+                    float part = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) part += y[i];
+                    const float mean = row_sum8(part) * (1.0f / kC);
+                    float var = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) var = fmaf(y[i] - mean, y[i] - mean, var);
+                    const float rstd = 1.0f / sqrtf(row_sum8(var) * (1.0f / kC) + P.ln_eps);
+                    float c1 = 0.f, c2 = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        y[i] = (y[i] - mean) * rstd;                          // x-hat
+                        p_gamma[i] = fmaf(dy[j][i], y[i], p_gamma[i]);
+                        p_beta[i] += dy[j][i];
+                        const float gy = dy[j][i] * gmc[i];
+                        c1 += gy;
+                        c2 = fmaf(gy, y[i], c2);
+                    }
+                    c1 = row_sum8(c1) * (1.0f / kC);
+                    c2 = row_sum8(c2) * (1.0f / kC);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) dy[j][i] = rstd * (dy[j][i] * gmc[i] - c1 - y[i] * c2);
+                }
+                // dscore_k = a_k (dy . m_k - sum_j a_j dy . m_j)
+                float da[3], dot = 0.f;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    float part = 0.f;
+                    if (k < n_msgs) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) part = fmaf(dy[j][i], mk[k][j][i], part);
+                    }
+                    da[k] = row_sum8(part);
+                    dot = fmaf(att[j][k], da[k], dot);
+                }
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    dsc[j][k] = (k < n_msgs && alive[j]) ? att[j][k] * (da[k] - dot) : 0.f;
+                    if (c == 0) p_b2 += dsc[j][k];
+                }
+                // dy crosses to the row map through shared memory.  Lanes 0..3 of a row store their first 16-byte
+                // chunk while lanes 4..7 store their second one (and vice versa): eight distinct bank groups.
+                const int rr = ra + 64 * j;
+                const float4 lo4 = make_float4(dy[j][0], dy[j][1], dy[j][2], dy[j][3]);
+                const float4 hi4 = make_float4(dy[j][4], dy[j][5], dy[j][6], dy[j][7]);
+                const bool first = c < 4;
+                *reinterpret_cast<float4*>(dy_s + dy_off(rr, 2 * c + (first ? 0 : 1))) = first ? lo4 : hi4;
+                *reinterpret_cast<float4*>(dy_s + dy_off(rr, 2 * c + (first ? 1 : 0))) = first ? hi4 : lo4;
+                // message 0 goes straight into its operand image (Q is idle: the previous tile's last round was awaited)
+                store_split8(q_img, kPart, rr, c, mk[0][j]);
             }
         }
 
         // ---------------- per message: two MMA rounds ----------------
-        float dx[kCW];
+        float dx[kCW];                                                        // row map
 #pragma unroll
-        for (int j = 0; j < kCW; ++j) dx[j] = 0.f;
-        float pre[kCW];
-        load_slice(P.saved_pre[0], row, col0, alive, pre);
+        for (int i = 0; i < kCW; ++i) dx[i] = 0.f;
+        const long long row = row0 + r;                                       // row map
+        const bool row_alive = row < live;
+        float pre[2][8];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) load_chunk(P.saved_pre[0], grow[j], c, alive[j], pre[j]);
 #pragma unroll 1
         for (int k = 0; k < n_msgs; ++k) {
-            const float dsk = k == 0 ? dsc[0] : (k == 1 ? dsc[1] : dsc[2]);
-            const float ak = k == 0 ? att[0] : (k == 1 ? att[1] : att[2]);
-            // dpre_k (evaluated while the previous round 2 is still running)
-            float ge[kCW];
-#pragma unroll
-            for (int j = 0; j < kCW; ++j) {
-                const float x = pre[j];
-                const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
-                const float pdf = 0.39894228040143267794f * expf(-0.5f * x * x);
-                ge[j] = dsk * (x * cdf);                           // dscore_k GELU(pre): w2 gradient term
-                pre[j] = dsk * w2r[j] * (cdf + x * pdf);           // dpre_k
-            }
-            p_w2 += colsum16(ge, lane);
-            p_b1 += colsum16(pre, lane);
+            float mq[2][8];
             if (k > 0) {
-                // round 2 of message k - 1: Ga -> g_agg_{k-1}
-                mbar_wait(&bar, parity);
+#pragma unroll
+                for (int j = 0; j < 2; ++j) load_chunk(P.saved_m[k], grow[j], c, alive[j], mq[j]);   // hidden behind the GELU math
+            }
+            // dpre_k (evaluated while the previous round 2 is still running)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const float dsk = k == 0 ? dsc[j][0] : (k == 1 ? dsc[j][1] : dsc[j][2]);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float x = pre[j][i];
+                    const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+                    const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
+                    p_w2[i] = fmaf(dsk, x * cdf, p_w2[i]);                    // dscore_k GELU(pre): w2 gradient
+                    const float d = dsk * w2c[i] * (cdf + x * pdf);           // dpre_k
+                    p_b1[i] += d;
+                    pre[j][i] = d;
+                }
+            }
+            if (k > 0) {
+                // round 2 of message k - 1: Ga -> g_agg_{k-1}   (row map)
+                mbar_wait_backoff(bar, parity);
                 parity ^= 1;
                 tc_fence_after_sync();
                 float ga[kCW];
                 tmem_ld16(tm_ga + lane_addr + col0, ga);
                 const float sp = k == 1 ? scale_r[0] : scale_r[1];
-                if (alive) {
+                if (row_alive) {
                     float4* dst = reinterpret_cast<float4*>(G.g_agg[k - 1] + row * kC + col0);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        dst[j] = make_float4(sp * ga[4 * j], sp * ga[4 * j + 1], sp * ga[4 * j + 2], sp * ga[4 * j + 3]);
+                    for (int i = 0; i < 4; ++i)
+                        dst[i] = make_float4(sp * ga[4 * i], sp * ga[4 * i + 1], sp * ga[4 * i + 2], sp * ga[4 * i + 3]);
                 }
             }
-            store_slice_image(p_img, r, q, pre);
-            {
-                float mk[kCW];
-                load_slice(P.saved_m[k], row, col0, alive, mk);
-                store_slice_image(q_img, r, q, mk);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                store_split8(p_img, kPart, ra + 64 * j, c, pre[j]);
+                if (k > 0) store_split8(q_img, kPart, ra + 64 * j, c, mq[j]);
             }
             fence_async_shared();
             tc_fence_before_sync();
             __syncthreads();
-            if (tid == 0) {
-                tc_fence_after_sync();
-                gemm_bf16x3(tm_t, k_major(p_s, kTileRows), mn_major(w1_s, kC, kWPart), idesc_bf16(128, 64, 0, 1), kC / 16, 0);
-                gemm_bf16x3(tm_dw1, mn_major(p_s, kTileRows, kPart), mn_major(q_s, kTileRows, kPart), idesc_bf16(128, 64, 1, 1),
-                            kTileRows / 16, (tiles_done | static_cast<uint32_t>(k)) != 0u);
-                mma_commit(&bar);
+            if (warp == 0) {
+                if (lane == 0) {
+                    tc_fence_after_sync();
+                    gemm_bf16x3_unrolled<kC / 16>(tm_t, k_major(p_s, kTileRows), mn_major(w1_s, kC, kWPart), idesc_bf16(128, 64, 0, 1), 0);
+                    gemm_bf16x3_unrolled<kTileRows / 16>(tm_dw1, mn_major(p_s, kTileRows, kPart), mn_major(q_s, kTileRows, kPart),
+                                                         idesc_bf16(64, 64, 1, 1), (tiles_done | static_cast<uint32_t>(k)) != 0u);
+                    mma_commit(bar);
+                }
+                __syncwarp();      // the other lanes park here instead of polling against the issuing lane
             }
-            float ag[kCW];
-            load_slice(P.agg[k], row, col0, alive, ag);
-            mbar_wait(&bar, parity);
+            float ag[2][8];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) load_chunk(P.agg[k], grow[j], c, alive[j], ag[j]);
+            // the row map's view of dy and a_k
+            float t[kCW];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float4 v = *reinterpret_cast<const float4*>(dy_s + dy_off(r, 4 * q + i));
+                t[4 * i] = v.x; t[4 * i + 1] = v.y; t[4 * i + 2] = v.z; t[4 * i + 3] = v.w;
+            }
+            const float ak = att_s[k * kTileRows + r];
+            mbar_wait_backoff(bar, parity);
             parity ^= 1;
             tc_fence_after_sync();
             {
-                float t[kCW];
-                tmem_ld16(tm_t + lane_addr + col0, t);
+                float tt[kCW];
+                tmem_ld16(tm_t + lane_addr + col0, tt);
+                float lo[8], hi[8];
 #pragma unroll
-                for (int j = 0; j < kCW; ++j) {
-                    t[j] = alive ? fmaf(ak, dy[j], t[j]) : 0.f;    // dm_k
-                    dx[j] += t[j];
+                for (int i = 0; i < 8; ++i) {
+                    lo[i] = row_alive ? fmaf(ak, t[i], tt[i]) : 0.f;          // dm_k
+                    hi[i] = row_alive ? fmaf(ak, t[8 + i], tt[8 + i]) : 0.f;
+                    dx[i] += lo[i];
+                    dx[8 + i] += hi[i];
                 }
-                store_slice_image(p_img, r, q, t);
+                store_split8(p_img, kPart, r, 2 * q, lo);
+                store_split8(p_img, kPart, r, 2 * q + 1, hi);
             }
-            store_slice_image(q_img, r, q, ag);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) store_split8(q_img, kPart, ra + 64 * j, c, ag[j]);
             fence_async_shared();
             tc_fence_before_sync();
             __syncthreads();
-            if (tid == 0) {
-                tc_fence_after_sync();
-                gemm_bf16x3(tm_ga, k_major(p_s, kTileRows), k_major(wk_s + k * kWImg, kC), idesc_bf16(128, 64, 0, 0), kC / 16, 0);
-                gemm_bf16x3(tm_dwp + k * 64, mn_major(q_s, kTileRows, kPart), mn_major(p_s, kTileRows, kPart),
-                            idesc_bf16(128, 64, 1, 1), kTileRows / 16, tiles_done != 0u);
-                mma_commit(&bar);
+            if (warp == 0) {
+                if (lane == 0) {
+                    tc_fence_after_sync();
+                    gemm_bf16x3_unrolled<kC / 16>(tm_ga, k_major(p_s, kTileRows), k_major(wk_s + k * kWImg, kC), idesc_bf16(128, 64, 0, 0), 0);
+                    gemm_bf16x3_unrolled<kTileRows / 16>(tm_dwp + k * 64, mn_major(q_s, kTileRows, kPart), mn_major(p_s, kTileRows, kPart),
+                                                         idesc_bf16(64, 64, 1, 1), tiles_done != 0u);
+                    mma_commit(bar);
+                }
+                __syncwarp();
             }
-            if (k + 1 < n_msgs) load_slice(P.saved_pre[k + 1], row, col0, alive, pre);
+            if (k + 1 < n_msgs) {
+#pragma unroll
+                for (int j = 0; j < 2; ++j) load_chunk(P.saved_pre[k + 1], grow[j], c, alive[j], pre[j]);
+            }
         }
         // round 2 of the last message
-        mbar_wait(&bar, parity);
+        mbar_wait_backoff(bar, parity);
         parity ^= 1;
         tc_fence_after_sync();
         {
             float ga[kCW];
             tmem_ld16(tm_ga + lane_addr + col0, ga);
             const float sp = n_msgs == 1 ? scale_r[0] : (n_msgs == 2 ? scale_r[1] : scale_r[2]);
-            if (alive) {
+            if (row_alive) {
                 float4* dst = reinterpret_cast<float4*>(G.g_agg[n_msgs - 1] + row * kC + col0);
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    dst[j] = make_float4(sp * ga[4 * j], sp * ga[4 * j + 1], sp * ga[4 * j + 2], sp * ga[4 * j + 3]);
+                for (int i = 0; i < 4; ++i)
+                    dst[i] = make_float4(sp * ga[4 * i], sp * ga[4 * i + 1], sp * ga[4 * i + 2], sp * ga[4 * i + 3]);
                 if (G.g_x != nullptr) {
                     float4* dxp = reinterpret_cast<float4*>(G.g_x + row * kC + col0);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) dxp[j] = make_float4(dx[4 * j], dx[4 * j + 1], dx[4 * j + 2], dx[4 * j + 3]);
+                    for (int i = 0; i < 4; ++i) dxp[i] = make_float4(dx[4 * i], dx[4 * i + 1], dx[4 * i + 2], dx[4 * i + 3]);
                 }
             }
         }
         tc_fence_before_sync();
+        __syncthreads();          // dy / a_k in shared memory are rewritten by the next tile's phase A
     }
 
     // ---------------- parameter gradients of this CTA ----------------
-    __syncthreads();
     tc_fence_after_sync();
-    if ((lane & 1) == 0) {
-        const int c = col0 + ((lane >> 1) & 15);
-        atomicAdd(G.g_att_b1 + c, p_b1);
-        atomicAdd(G.g_att_w2 + c, p_w2);
-        if (apply_ln) {
-            atomicAdd(G.g_ln_gamma + c, p_gamma);
-            atomicAdd(G.g_ln_beta + c, p_beta);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        // fold the four row groups of the warp (lanes with equal c): lanes 0..7 then hold the warp's column sums
+        p_b1[i] += __shfl_xor_sync(0xffffffffu, p_b1[i], 8);
+        p_b1[i] += __shfl_xor_sync(0xffffffffu, p_b1[i], 16);
+        p_w2[i] += __shfl_xor_sync(0xffffffffu, p_w2[i], 8);
+        p_w2[i] += __shfl_xor_sync(0xffffffffu, p_w2[i], 16);
+        p_gamma[i] += __shfl_xor_sync(0xffffffffu, p_gamma[i], 8);
+        p_gamma[i] += __shfl_xor_sync(0xffffffffu, p_gamma[i], 16);
+        p_beta[i] += __shfl_xor_sync(0xffffffffu, p_beta[i], 8);
+        p_beta[i] += __shfl_xor_sync(0xffffffffu, p_beta[i], 16);
+    }
+    {
+        // one atomic per column and CTA: the 16 warps meet in shared memory first (the dy tile is idle now)
+        float* part = reinterpret_cast<float*>(dy_s);          // [16 warps][4 quantities][64 columns]
+        if (lane < 8) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                part[(warp * 4 + 0) * kC + 8 * c + i] = p_b1[i];
+                part[(warp * 4 + 1) * kC + 8 * c + i] = p_w2[i];
+                part[(warp * 4 + 2) * kC + 8 * c + i] = p_gamma[i];
+                part[(warp * 4 + 3) * kC + 8 * c + i] = p_beta[i];
+            }
+        }
+        __syncthreads();
+        if (tid < 4 * kC) {
+            const int which = tid >> 6, col = tid & 63;
+            float sum = 0.f;
+#pragma unroll
+            for (int w = 0; w < kThreads / 32; ++w) sum += part[(w * 4 + which) * kC + col];
+            float* dst = which == 0 ? G.g_att_b1 : (which == 1 ? G.g_att_w2 : (which == 2 ? G.g_ln_gamma : G.g_ln_beta));
+            if (which < 2 || apply_ln) atomicAdd(dst + col, sum);
         }
     }
-    if (q == 0) {
-        p_b2 = warp_sum(p_b2);
-        if (lane == 0 && p_b2 != 0.f) atomicAdd(G.g_att_b2, p_b2);
-    }
-    if ((warp & 3) < 2) {
-        // accumulator rows 0..63 live in lanes 0..63; warp group g = warp / 4 drains DW1 (g = 0) or DWp_{g-1}
+    p_b2 = warp_sum(p_b2);
+    if (lane == 0 && p_b2 != 0.f) atomicAdd(G.g_att_b2, p_b2);
+    {
+        // M = 64 accumulators: row i lives in lane 32 (i / 16) + i % 16, i.e. lanes 0..15 of every lane quarter;
+        // warp group g = warp / 4 drains DW1 (g = 0) or DWp_{g-1}
         const int g = warp >> 2;
-        const int drow = (warp & 3) * 32 + lane;
+        const int drow = (warp & 3) * 16 + (lane & 15);
         float* dst = g == 0 ? G.g_att_w1 : (g - 1 < n_msgs ? G.g_wprod[g - 1] : nullptr);
         if (dst != nullptr) {
             const uint32_t src = (g == 0 ? tm_dw1 : tm_dwp + (g - 1) * 64) + lane_addr;
@@ -391,8 +438,10 @@ __global__ void __launch_bounds__(kThreads, 1) combine_bwd_fused_kernel(topo_com
             for (int c8 = 0; c8 < 8; ++c8) {
                 float v[8];
                 tmem_ld8(src + c8 * 8, v);
+                if (lane < 16) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) atomicAdd(dst + drow * kC + c8 * 8 + i, v[i]);
+                    for (int i = 0; i < 8; ++i) atomicAdd(dst + drow * kC + c8 * 8 + i, v[i]);
+                }
             }
         }
     }
@@ -421,7 +470,7 @@ extern "C" int topo_sccn_combine_bwd_tc(const topo_combine_params* p, int64_t ro
     TOPO_REQUIRE(p->att_w1 && p->att_w2 && g->g_att_w1 && g->g_att_b1 && g->g_att_w2 && g->g_att_b2, "null attention parameter");
     TOPO_REQUIRE(!p->apply_ln || (p->ln_gamma && g->g_ln_gamma && g->g_ln_beta), "null LayerNorm parameter");
     if (rows == 0) return TOPO_OK;
-    const size_t smem = BwdSmem::kTotal + 1024;
+    const size_t smem = BwdSmem::kTotal;
     if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(combine_bwd_fused_kernel), smem)) return rc;
     const int tiles = static_cast<int>((rows + kTileRows - 1) / kTileRows);
     combine_bwd_fused_kernel<<<std::min(tiles, sm_count()), kThreads, smem, as_stream(stream)>>>(*p, rows, n_rows_dev, grad_out, *g);

@@ -282,12 +282,15 @@ __global__ void __launch_bounds__(128 * NQ, 1) combine_fwd_tc_kernel(topo_combin
             if (k + 1 < n_msgs) prefetch(P.agg[k + 1], row0);
             else if (tile + gridDim.x < tiles) prefetch(P.agg[0], (tile + gridDim.x) * kTileRows);
             __syncthreads();                                                    // S1: A = agg_k is staged
-            if (tid == 0) {
-                tc_fence_after_sync();
-                gemm_128x64x64_3xtf32(tmem_base + k * kC, a_hi_s, a_lo_s, w_s + (2 * k) * kBTile, w_s + (2 * k + 1) * kBTile, 0);
-                mma_commit(&bar);
+            if (warp == 0) {
+                if (tid == 0) {
+                    tc_fence_after_sync();
+                    gemm_128x64x64_3xtf32(tmem_base + k * kC, a_hi_s, a_lo_s, w_s + (2 * k) * kBTile, w_s + (2 * k + 1) * kBTile, 0);
+                    mma_commit(&bar);
+                }
+                __syncwarp();      // the other lanes park here instead of polling against the issuing lane
             }
-            mbar_wait(&bar, parity);
+            mbar_wait_backoff(&bar, parity);
             parity ^= 1;
             tc_fence_after_sync();
             // epilogue 1: m_k = scale_k T_k + x, re-staged as the A operand of the attention GEMM
@@ -311,12 +314,15 @@ __global__ void __launch_bounds__(128 * NQ, 1) combine_fwd_tc_kernel(topo_combin
             fence_async_shared();
             tc_fence_before_sync();
             __syncthreads();                                                    // S2: A = m_k is staged
-            if (tid == 0) {
-                tc_fence_after_sync();
-                gemm_128x64x64_3xtf32(tmem_base + 3 * kC, a_hi_s, a_lo_s, w_s + 6 * kBTile, w_s + 7 * kBTile, 0);
-                mma_commit(&bar);
+            if (warp == 0) {
+                if (tid == 0) {
+                    tc_fence_after_sync();
+                    gemm_128x64x64_3xtf32(tmem_base + 3 * kC, a_hi_s, a_lo_s, w_s + 6 * kBTile, w_s + 7 * kBTile, 0);
+                    mma_commit(&bar);
+                }
+                __syncwarp();
             }
-            mbar_wait(&bar, parity);
+            mbar_wait_backoff(&bar, parity);
             parity ^= 1;
             tc_fence_after_sync();
             // epilogue 2: this half-row's share of the attention score

@@ -101,5 +101,25 @@ __device__ __forceinline__ void gemm_bf16x3(uint32_t tmem_d, const Operand& a, c
     }
 }
 
+// Same product with the pass / k-step structure known at compile time: the issuing thread executes one
+// 32-bit add per operand and the MMA itself (the descriptor's 14-bit start-address field advances by the byte
+// offset >> 4; shared-memory addresses stay below 256 KB, so the add never carries out of the field).
+template <int KSTEPS>
+__device__ __forceinline__ void gemm_bf16x3_unrolled(uint32_t tmem_d, const Operand& a, const Operand& b, uint32_t idesc,
+                                                     uint32_t accumulate_into) {
+    const uint64_t a0 = smem_desc_sw128(a.base, a.lbo, a.sbo), b0 = smem_desc_sw128(b.base, b.lbo, b.sbo);
+    uint32_t acc = accumulate_into;
+#pragma unroll
+    for (int pass = 0; pass < 6; ++pass) {
+        const uint32_t pa = pass == 0 ? 2u : ((pass == 2 || pass == 3) ? 1u : 0u);
+        const uint32_t pb = pass == 1 ? 2u : ((pass == 2 || pass == 4) ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < KSTEPS; ++k) {
+            mma_bf16(tmem_d, a0 + ((pa * a.part_stride + k * a.kstep) >> 4), b0 + ((pb * b.part_stride + k * b.kstep) >> 4), idesc, acc);
+            acc = 1;
+        }
+    }
+}
+
 }  // namespace tc16
 }  // namespace topo
