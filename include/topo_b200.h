@@ -240,7 +240,19 @@ typedef struct {
     /* Optional [3, rows] attention scores Linear2(GELU(pre_k)) (NULL = not used).  Written by
      * topo_sccn_combine_fwd_tc; required by topo_sccn_combine_bwd_tc, which then evaluates erf once. */
     float* saved_score;
+    /* Memory layout of saved_m / saved_pre.  TOPO_SAVED_ROW_MAJOR: [rows, C].  TOPO_SAVED_TILE_FRAGMENT: a
+     * permutation inside every 128-row tile that makes the tensor-core kernels' accesses contiguous
+     * (csrc/layout.cuh); the buffers then hold rows rounded up to a multiple of 128.  topo_sccn_combine_fwd_tc2
+     * writes (only) the tile-fragment layout; topo_sccn_combine_bwd_tc reads either. */
+    int saved_layout;
+    /* Optional (channels == 64): this rank's weight images from topo_sccn_prepare_images, laid out as
+     *   [ W1 image | message 0: W image, V image | message 1: ... ]   (24 KB each)
+     * When NULL the tensor-core kernels build the images themselves (about 30 us of set-up per launch). */
+    const void* weight_images;
 } topo_combine_params;
+
+#define TOPO_SAVED_ROW_MAJOR 0
+#define TOPO_SAVED_TILE_FRAGMENT 1
 
 typedef struct {
     float* g_agg[3];         /* [rows, C] overwritten */
@@ -255,12 +267,31 @@ typedef struct {
     float* g_ln_beta;
 } topo_combine_grads;
 
+/* bf16x3 operand images of the weights (csrc/weight_images.cu), built once per layer and step and shared by the
+ * forward and backward tensor-core kernels of all ranks.  A job with `w` writes the image of W_k [in][out]
+ * (24,576 bytes) followed by the image of V_k = s_k W_k W1^T (24,576 bytes) to dst; a job with w == NULL writes
+ * the image of W1 [out][in] (24,576 bytes).  At most 16 jobs per call, one CTA each. */
+typedef struct {
+    const float* w;
+    const float* scale;
+    const float* att_w1;
+    void* dst;
+} topo_image_job;
+#define TOPO_WEIGHT_IMAGE_BYTES 24576
+int topo_sccn_prepare_images(const topo_image_job* jobs, int n_jobs, int channels, topo_stream_t stream);
+
 int topo_sccn_combine_fwd(const topo_combine_params* p, int64_t rows, const int32_t* n_rows_dev,
                           float* out, topo_stream_t stream);
 /* Same contract, channels == 64 only: the GEMMs run on the tensor cores (tcgen05.mma kind::tf32, 3xTF32
  * operand splitting for fp32-level accuracy, accumulators in tensor memory), 128-row tiles. */
 int topo_sccn_combine_fwd_tc(const topo_combine_params* p, int64_t rows, const int32_t* n_rows_dev,
                              float* out, topo_stream_t stream);
+/* Second-generation tensor-core forward (channels == 64): bf16x3 operand images, ONE 128 x 128 x 64 product
+ * per message ([agg_k W_k | agg_k (s_k W_k W1^T)], no dependent GEMM chain), double-buffered operand slots and
+ * accumulators, saved activations in the tile-fragment layout (always written: saved_m, saved_pre,
+ * saved_score must be set and saved_layout == TOPO_SAVED_TILE_FRAGMENT).  csrc/combine_fwd16.cu */
+int topo_sccn_combine_fwd_tc2(const topo_combine_params* p, int64_t rows, const int32_t* n_rows_dev,
+                              float* out, topo_stream_t stream);
 /* workspace: n_msgs * rows * C floats (dL/dm_k between the two backward kernels).
  * _attention: LayerNorm, softmax and attention-MLP backward -> dL/dm_k (workspace), g_x, attention and
  *             LayerNorm parameter gradients.  _conv: dL/dagg_k and g_wprod from the workspace.

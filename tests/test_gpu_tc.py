@@ -238,3 +238,99 @@ def test_fused_tensor_core_backward_matches_fp64_autograd(n_msgs, apply_ln, rows
     if apply_ln:
         check_one("gamma", fused["gamma"], two_kernel["gamma"], gam.grad)
         check_one("beta", fused["beta"], two_kernel["beta"], bet.grad)
+
+
+@pytest.mark.parametrize("n_msgs,apply_ln,rows,residual", [(3, True, 1000, True), (2, False, 130, True), (1, True, 64, False),
+                                                            (2, True, 40000, True), (3, False, 5000, True), (2, True, 257, False)])
+def test_second_generation_forward_and_its_backward(n_msgs, apply_ln, rows, residual):
+    """topo_sccn_combine_fwd_tc2 (bf16x3, one product per message, tile-fragment saves) against fp64, with the
+    FFMA forward as the accuracy yardstick; then the fused backward on its tile-fragment saves against the same
+    backward on the first-generation forward's row-major saves (two layouts, one result)."""
+    import ctypes as C
+    from topo_audio_autoencoder_b200._lib import lib, check, ptr, stream, CombineGrads
+    from topo_audio_autoencoder_b200.custom_sccn import _make_params
+    g = torch.Generator().manual_seed(rows * 5 + n_msgs)
+    ch = 64
+    rnd = lambda *s: torch.randn(*s, generator=g).cuda()     # noqa: E731
+    aggs = [rnd(rows, ch) * 2 for _ in range(n_msgs)]
+    ws = [rnd(ch, ch) * 0.2 for _ in range(n_msgs)]
+    scales = [torch.tensor([0.7 + 0.2 * k]).cuda() for k in range(n_msgs)]
+    x = rnd(rows, ch) if residual else None
+    tensors = [rnd(ch, ch) * 0.2, rnd(ch) * 0.1, rnd(ch) * 0.3, rnd(1), 1 + 0.1 * rnd(ch), 0.1 * rnd(ch)]
+    g_out = rnd(rows, ch)
+    live_n = rows - 3 if rows > 100 else rows
+    live = torch.tensor([live_n], dtype=torch.int32).cuda()
+    rows_pad = -(-rows // 128) * 128
+
+    def forward(gen):
+        pad = rows_pad if gen == 2 else rows
+        saved = ([torch.zeros(pad, ch, device="cuda") for _ in range(n_msgs)],
+                 [torch.zeros(pad, ch, device="cuda") for _ in range(n_msgs)], torch.zeros(3, rows, device="cuda"))
+        params = _make_params(ch, n_msgs, aggs, ws, scales, x, tensors, 1e-5, apply_ln, saved, gen == 2)
+        out = torch.zeros(rows, ch, device="cuda")
+        fn = {0: lib.topo_sccn_combine_fwd, 1: lib.topo_sccn_combine_fwd_tc, 2: lib.topo_sccn_combine_fwd_tc2}[gen]
+        check(fn(C.byref(params), rows, ptr(live, torch.int32), ptr(out), stream()))
+        torch.cuda.synchronize()
+        return out, params, saved
+
+    out0, _, _ = forward(0)
+    out1, params1, saved1 = forward(1)
+    out2, params2, saved2 = forward(2)
+    m = [s.double() * (a.double() @ w.double()) + (x.double() if residual else 0) for a, w, s in zip(aggs, ws, scales)]
+    w1, b1, w2, b2, gam, bet = (t.double() for t in tensors)
+    pre = [mk @ w1.t() + b1 for mk in m]
+    sc = torch.stack([torch.nn.functional.gelu(p_) @ w2 + b2 for p_ in pre])
+    att = torch.softmax(sc, dim=0)
+    ref = sum(att[k].unsqueeze(1) * m[k] for k in range(n_msgs))
+    if apply_ln:
+        ref = torch.nn.functional.layer_norm(ref, (ch,), gam, bet, 1e-5)
+    ref[live_n:] = 0
+    e0 = (out0.double() - ref).abs().max().item()
+    e2 = (out2.double() - ref).abs().max().item()
+    report(f"tc/fwd2/out/msgs={n_msgs}/ln={apply_ln}/rows={rows}", out2, ref.float())
+    assert torch.isfinite(out2).all()
+    assert e2 <= 4 * e0 + 1e-6, f"second-generation forward error {e2:.3e} vs FFMA error {e0:.3e} (both against fp64)"
+    assert (out2[live_n:] == 0).all(), "rows past the live count must not be touched"
+    # the saved tensors, un-permuted: element (row, col) sits at tile*8192 + ((col//16*4 + col%16//4)*128 + row%128)*4 + col%4
+    rr = torch.arange(rows_pad, device="cuda").unsqueeze(1)
+    cc = torch.arange(ch, device="cuda").unsqueeze(0)
+    pos = (rr // 128) * 8192 + ((cc // 16 * 4 + cc % 16 // 4) * 128 + rr % 128) * 4 + cc % 4
+    for k in range(n_msgs):
+        got_m = saved2[0][k].reshape(-1)[pos][:live_n]
+        got_p = saved2[1][k].reshape(-1)[pos][:live_n]
+        report(f"tc/fwd2/saved_m{k}/msgs={n_msgs}/rows={rows}", got_m, m[k][:live_n].float())
+        assert (got_m.double() - m[k][:live_n]).abs().max().item() <= 2e-6 * m[k].abs().max().item() + 1e-6
+        assert (got_p.double() - pre[k][:live_n]).abs().max().item() <= 2e-6 * pre[k].abs().max().item() + 2e-6
+        assert (saved2[2][k][:live_n].double() - sc[k][:live_n]).abs().max().item() <= 4e-6 * sc.abs().max().item() + 2e-6
+
+    def backward(params):
+        res = {"g_agg": [torch.zeros(rows, ch, device="cuda") for _ in range(n_msgs)],
+               "wprod": [torch.zeros(ch, ch, device="cuda") for _ in range(n_msgs)],
+               "g_x": torch.zeros(rows, ch, device="cuda") if residual else None,
+               "w1": torch.zeros(ch, ch, device="cuda"), "b1": torch.zeros(ch, device="cuda"),
+               "w2": torch.zeros(ch, device="cuda"), "b2": torch.zeros(1, device="cuda"),
+               "gamma": torch.zeros(ch, device="cuda"), "beta": torch.zeros(ch, device="cuda")}
+        grads = CombineGrads()
+        for k in range(n_msgs):
+            grads.g_agg[k], grads.g_wprod[k] = ptr(res["g_agg"][k]), ptr(res["wprod"][k])
+        grads.g_x = ptr(res["g_x"])
+        grads.g_att_w1, grads.g_att_b1, grads.g_att_w2, grads.g_att_b2 = ptr(res["w1"]), ptr(res["b1"]), ptr(res["w2"]), ptr(res["b2"])
+        grads.g_ln_gamma, grads.g_ln_beta = ptr(res["gamma"]), ptr(res["beta"])
+        check(lib.topo_sccn_combine_bwd_tc(C.byref(params), rows, ptr(live, torch.int32), ptr(g_out), C.byref(grads), stream()))
+        torch.cuda.synchronize()
+        return res
+
+    b1_, b2_ = backward(params1), backward(params2)
+    for name in ("g_agg", "wprod"):
+        for k in range(n_msgs):
+            a_, b_ = b1_[name][k], b2_[name][k]
+            tol = 2e-5 * a_.abs().max().item() + 1e-6
+            assert (a_ - b_).abs().max().item() <= tol, (name, k, (a_ - b_).abs().max().item(), tol)
+    for name in ("g_x", "w1", "b1", "w2", "b2", "gamma", "beta"):
+        a_, b_ = b1_[name], b2_[name]
+        if a_ is None or (name in ("gamma", "beta") and not apply_ln):
+            continue
+        tol = 2e-5 * a_.abs().max().item() + 2e-6
+        if name == "b2":      # softmax is shift invariant: the exact gradient is 0 and both values are pure round-off
+            tol = 1e-4
+        assert (a_ - b_).abs().max().item() <= tol, (name, (a_ - b_).abs().max().item(), tol)

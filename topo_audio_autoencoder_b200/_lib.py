@@ -35,7 +35,15 @@ class CombineParams(C.Structure):
                 ("att_w2", C.c_void_p), ("att_b2", C.c_void_p),
                 ("ln_gamma", C.c_void_p), ("ln_beta", C.c_void_p),
                 ("ln_eps", C.c_float), ("apply_ln", C.c_int),
-                ("saved_m", C.c_void_p * 3), ("saved_pre", C.c_void_p * 3), ("saved_score", C.c_void_p)]
+                ("saved_m", C.c_void_p * 3), ("saved_pre", C.c_void_p * 3), ("saved_score", C.c_void_p), ("saved_layout", C.c_int), ("weight_images", C.c_void_p)]
+
+
+class ImageJob(C.Structure):
+    """topo_image_job"""
+    _fields_ = [("w", C.c_void_p), ("scale", C.c_void_p), ("att_w1", C.c_void_p), ("dst", C.c_void_p)]
+
+
+WEIGHT_IMAGE_BYTES = 24576
 
 
 class CombineGrads(C.Structure):
@@ -80,8 +88,10 @@ SIGNATURES = {
     "topo_sccn_aggregate_bwd": [_P, C.POINTER(ComplexView), _I32, _PP, _PP, _PP, _PP, _PP, _PP, _PP, _P, _P],
     "topo_spmm_csr": [_I64, _P, _P, _P, _P, _I32, _P, _P],
     "topo_sddmm_csr": [_I64, _P, _P, _P, _P, _I32, _P, _P],
+    "topo_sccn_prepare_images": [C.POINTER(ImageJob), _I32, _I32, _P],
     "topo_sccn_combine_fwd": [C.POINTER(CombineParams), _I64, _P, _P, _P],
     "topo_sccn_combine_fwd_tc": [C.POINTER(CombineParams), _I64, _P, _P, _P],
+    "topo_sccn_combine_fwd_tc2": [C.POINTER(CombineParams), _I64, _P, _P, _P],
     "topo_sccn_combine_bwd": [C.POINTER(CombineParams), _I64, _P, _P, C.POINTER(CombineGrads), _P, _P],
     "topo_sccn_combine_bwd_attention": [C.POINTER(CombineParams), _I64, _P, _P, C.POINTER(CombineGrads), _P, _P],
     "topo_sccn_combine_bwd_conv": [C.POINTER(CombineParams), _I64, _P, C.POINTER(CombineGrads), _P, _P],
@@ -117,7 +127,7 @@ KERNELS_PER_CALL = {
     "topo_active_sets": 2, "topo_penalties_fwd": 1, "topo_penalties_bwd": 1, "topo_embed_fwd": 1,
     "topo_embed_bwd": 2, "topo_layernorm_fwd": 1, "topo_layernorm_bwd": 1, "topo_operators_count": 2,
     "topo_operators_fill": 1, "topo_operators_bwd": 1, "topo_sccn_aggregate_fwd": 2, "topo_sccn_aggregate_bwd": 2,
-    "topo_spmm_csr": 1, "topo_sddmm_csr": 1, "topo_sccn_combine_fwd": 1, "topo_sccn_combine_fwd_tc": 1, "topo_sccn_combine_bwd": 2,
+    "topo_spmm_csr": 1, "topo_sddmm_csr": 1, "topo_sccn_prepare_images": 1, "topo_sccn_combine_fwd": 1, "topo_sccn_combine_fwd_tc": 1, "topo_sccn_combine_fwd_tc2": 1, "topo_sccn_combine_bwd": 2,
     "topo_sccn_combine_bwd_attention": 1, "topo_sccn_combine_bwd_conv": 1, "topo_sccn_combine_bwd_conv_tc": 1, "topo_sccn_combine_bwd_tc": 1, "topo_distance_prepare": 1,
     "topo_distance_rows": 1, "topo_debug_gemm_tf32x3": 1, "topo_debug_gemm_bf16x3": 1,
 }

@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 OUT = os.path.join(os.path.dirname(HERE), "libtopo_b200.so")
 STAMP = OUT + ".stamp"
-SOURCES = ["tables.cu", "gate.cu", "rectifier.cu", "operators.cu", "aggregate.cu", "combine.cu", "combine_tc.cu", "combine_bwd_tc.cu", "gemm16_debug.cu", "distance.cu"]
+SOURCES = ["tables.cu", "gate.cu", "rectifier.cu", "operators.cu", "aggregate.cu", "combine.cu", "combine_tc.cu", "weight_images.cu", "combine_fwd16.cu", "combine_bwd_tc.cu", "gemm16_debug.cu", "distance.cu"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
          "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
          "-I", os.path.join(ROOT, "include"), "-I", HERE]

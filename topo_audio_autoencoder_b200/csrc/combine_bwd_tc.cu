@@ -21,6 +21,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "layout.cuh"
 #include "tc16.cuh"
 
 namespace topo {
@@ -70,6 +71,22 @@ __device__ __forceinline__ void load_chunk(const float* __restrict__ src, long l
         const float4* p = reinterpret_cast<const float4*>(src + row * kC) + chunk * 2;
         a = __ldg(p);
         b = __ldg(p + 1);
+    }
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+
+// the same eight columns of a saved activation, in either layout (topo_combine_params.saved_layout)
+__device__ __forceinline__ void load_saved(const float* __restrict__ src, bool tile_fragment, long long row0, int tile_row, int chunk,
+                                           bool ok, float (&v)[8]) {
+    if (!tile_fragment) {
+        load_chunk(src, row0 + tile_row, chunk, ok, v);
+        return;
+    }
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    if (ok) {
+        const float4* p = reinterpret_cast<const float4*>(src) + tf_index_chunk(row0, tile_row, chunk);
+        a = __ldg(p);
+        b = __ldg(p + kTileRows);
     }
     v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
 }
@@ -125,14 +142,28 @@ __global__ void __launch_bounds__(kThreads, 1) combine_bwd_fused_kernel(topo_com
     const int c = tid & 7, ra = tid >> 3;                       // chunk map: rows ra and ra + 64
     const int n_msgs = P.n_msgs;
     const bool apply_ln = P.apply_ln != 0;
+    const bool tf = P.saved_layout == TOPO_SAVED_TILE_FRAGMENT;
 
     if (tid == 0) {
         mbar_init(bar, 1);
         fence_barrier_init();
     }
     if (warp == 0) tmem_alloc(tmem_base_smem, 512);
-    stage_weight16(P.att_w1, base + BwdSmem::kW1, tid);
-    for (int k = 0; k < n_msgs; ++k) stage_weight16(P.w[k], base + BwdSmem::kWk + k * kWImg, tid);
+    if (P.weight_images != nullptr) {
+        // images built once per layer (weight_images.cu): [W1 | k: W_k, V_k]; the backward uses W1 and the W_k
+        const uint4* __restrict__ src = reinterpret_cast<const uint4*>(P.weight_images);
+        constexpr int kImg16 = static_cast<int>(kWImg / 16);
+        uint4* d1 = reinterpret_cast<uint4*>(base + BwdSmem::kW1);
+        for (int idx = tid; idx < kImg16; idx += kThreads) d1[idx] = __ldg(src + idx);
+        for (int k = 0; k < n_msgs; ++k) {
+            uint4* dk = reinterpret_cast<uint4*>(base + BwdSmem::kWk + k * kWImg);
+            const uint4* sk = src + kImg16 * (1 + 2 * k);
+            for (int idx = tid; idx < kImg16; idx += kThreads) dk[idx] = __ldg(sk + idx);
+        }
+    } else {
+        stage_weight16(P.att_w1, base + BwdSmem::kW1, tid);
+        for (int k = 0; k < n_msgs; ++k) stage_weight16(P.w[k], base + BwdSmem::kWk + k * kWImg, tid);
+    }
     for (int i = tid; i < kC; i += kThreads) {
         vecs[i] = __ldg(P.att_w2 + i);
         vecs[kC + i] = apply_ln ? __ldg(P.ln_gamma + i) : 1.f;
@@ -171,7 +202,7 @@ __global__ void __launch_bounds__(kThreads, 1) combine_bwd_fused_kernel(topo_com
                 load_chunk(grad_out, grow[j], c, alive[j], dy[j]);
 #pragma unroll
                 for (int k = 0; k < 3; ++k)
-                    if (k < n_msgs) load_chunk(P.saved_m[k], grow[j], c, alive[j], mk[k][j]);
+                    if (k < n_msgs) load_saved(P.saved_m[k], tf, row0, ra + 64 * j, c, alive[j], mk[k][j]);
             }
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
@@ -260,13 +291,13 @@ __global__ void __launch_bounds__(kThreads, 1) combine_bwd_fused_kernel(topo_com
         const bool row_alive = row < live;
         float pre[2][8];
 #pragma unroll
-        for (int j = 0; j < 2; ++j) load_chunk(P.saved_pre[0], grow[j], c, alive[j], pre[j]);
+        for (int j = 0; j < 2; ++j) load_saved(P.saved_pre[0], tf, row0, ra + 64 * j, c, alive[j], pre[j]);
 #pragma unroll 1
         for (int k = 0; k < n_msgs; ++k) {
             float mq[2][8];
             if (k > 0) {
 #pragma unroll
-                for (int j = 0; j < 2; ++j) load_chunk(P.saved_m[k], grow[j], c, alive[j], mq[j]);   // hidden behind the GELU math
+                for (int j = 0; j < 2; ++j) load_saved(P.saved_m[k], tf, row0, ra + 64 * j, c, alive[j], mq[j]);   // hidden behind the GELU math
             }
             // dpre_k (evaluated while the previous round 2 is still running)
 #pragma unroll
@@ -275,8 +306,8 @@ __global__ void __launch_bounds__(kThreads, 1) combine_bwd_fused_kernel(topo_com
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const float x = pre[j][i];
-                    const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
-                    const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
+                    float cdf, pdf;
+                    gelu_cdf_pdf(x, cdf, pdf);
                     p_w2[i] = fmaf(dsk, x * cdf, p_w2[i]);                    // dscore_k GELU(pre): w2 gradient
                     const float d = dsk * w2c[i] * (cdf + x * pdf);           // dpre_k
                     p_b1[i] += d;
@@ -361,7 +392,7 @@ __global__ void __launch_bounds__(kThreads, 1) combine_bwd_fused_kernel(topo_com
             }
             if (k + 1 < n_msgs) {
 #pragma unroll
-                for (int j = 0; j < 2; ++j) load_chunk(P.saved_pre[k + 1], grow[j], c, alive[j], pre[j]);
+                for (int j = 0; j < 2; ++j) load_saved(P.saved_pre[k + 1], tf, row0, ra + 64 * j, c, alive[j], pre[j]);
             }
         }
         // round 2 of the last message

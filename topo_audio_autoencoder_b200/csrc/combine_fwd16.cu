@@ -1,0 +1,453 @@
+// S1 (b) forward on the tensor cores, second generation (C = 64): bf16x3 operand images (tc16.cuh), one MMA
+// round per message with NO dependent GEMM chain, operand slots and accumulators double-buffered so the
+// tensor pipe works underneath the epilogue of the previous message.
+//
+// The attention hidden layer of message k is  pre_k = W1 m_k + b1  with  m_k = s_k (agg_k W_k) + x.  Folding
+// the two products,  pre_k = agg_k (s_k W_k W1^T) + (x W1^T + b1) = agg_k V_k + H0 + b1,  both GEMMs of a message
+// read the SAME operand agg_k:   [ D1_k | H_k ] = agg_k [ W_k | V_k ]   is one 128 x 128 x 64 product, and
+// H0 = x W1^T is one more product per tile.  V_k (64 x 64) is formed once per CTA in fp32.
+//
+// Units of a tile: X (stages x, issues H0), then one unit per message (stages agg_k, issues [D1|H]).  The loop
+// is software-pipelined by one unit: stage u+1 and issue its MMA, then run the epilogue of unit u.
+//   stage    (chunk map)  thread t owns columns [8c, 8c+8), c = t % 8, of tile rows t/8 and t/8 + 64: coalesced
+//                         128-bit loads, prefetched one unit ahead into registers, split into the bf16x3 image
+//   epilogue (row map)    thread (q, r) = (t / 128, t % 128) owns columns [16q, 16q+16) of row r = TMEM lane r:
+//                         m_k = s_k D1 + x,  pre_k = H + H0 + b1,  partial score  sum GELU(pre) w2
+//   tile end              scores meet in shared memory, softmax, mix, LayerNorm, store
+// m_k, pre_k and the scores are SAVED for the backward in the tile-fragment layout (layout.cuh): every store and
+// every later load of these private tensors is a fully coalesced 128-bit access from the row map.
+#include <algorithm>
+
+#include "common.cuh"
+#include "layout.cuh"
+#include "tc16.cuh"
+
+namespace topo {
+namespace {
+
+using namespace tc16;
+
+constexpr int kTileRows = 128;
+constexpr int kC = 64;
+constexpr int kWorkers = 512;                             // 16 warps of stage / epilogue threads
+constexpr int kThreads = kWorkers + 32;                   // + one warp that only issues the MMAs
+constexpr int kCW = 16;
+constexpr uint32_t kPart = kTileRows * 128;               // 16 KB
+constexpr uint32_t kImg = 3 * kPart;                      // 48 KB
+constexpr uint32_t kWPart = kC * 128;                     // 8 KB
+constexpr uint32_t kWImg = 3 * kWPart;                    // 24 KB
+
+struct FwdSmem16 {
+    static constexpr uint32_t kA0 = 0;                    // operand slot 0
+    static constexpr uint32_t kW1 = kImg;                 // W1 [o][i]
+    static constexpr uint32_t kWV = kW1 + kWImg;          // per message: W_k [in][out] then V_k [in][hidden] (48 KB)
+    static constexpr uint32_t kA1 = kWV + 2 * 2 * kWImg;  // operand slot 1 = the third message's weights (n_msgs < 3 only)
+    static constexpr uint32_t kVec = kWV + 3 * 2 * kWImg; // b1, w2, gamma, beta
+    static constexpr uint32_t kRed = kVec + 4 * kC * 4;   // [4 slots][4 column groups][128 rows]
+    static constexpr uint32_t kBar = kRed + 4 * 4 * kTileRows * 4;
+    static constexpr uint32_t kTotal = kBar + 32;
+};
+static_assert(FwdSmem16::kA1 % 1024 == 0 && FwdSmem16::kTotal <= 232448, "shared-memory layout");
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ void load_chunk(const float* __restrict__ src, long long row, int chunk, bool ok, float (&v)[8]) {
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    if (ok) {
+        const float4* p = reinterpret_cast<const float4*>(src + row * kC) + chunk * 2;
+        a = ldg_pinned(p);
+        b = ldg_pinned(p + 1);
+    }
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+
+__global__ void __launch_bounds__(kThreads, 1) combine_fwd16_kernel(topo_combine_params P, long long rows,
+                                                                    const int* __restrict__ n_rows_dev,
+                                                                    float* __restrict__ out, int dbg, unsigned long long* __restrict__ stamps) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* base = smem_raw;
+    float* vecs = reinterpret_cast<float*>(base + FwdSmem16::kVec);
+    float* red = reinterpret_cast<float*>(base + FwdSmem16::kRed);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(base + FwdSmem16::kBar);       // one per operand slot
+    uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(base + FwdSmem16::kBar + 16);
+
+    auto stamp = [&](int slot) {
+        if (stamps != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            stamps[slot] = t;
+        }
+    };
+    stamp(0);
+    const long long live = n_rows_dev ? min(static_cast<long long>(*n_rows_dev), rows) : rows;
+    const long long tiles = (live + kTileRows - 1) / kTileRows;
+    if (blockIdx.x >= tiles) return;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int q = tid >> 7, r = tid & 127, col0 = q * kCW;     // row map
+    const int c = tid & 7, ra = tid >> 3;                       // chunk map: rows ra and ra + 64
+    const int n_msgs = P.n_msgs;
+    const bool has_x = P.x != nullptr;
+    const int n_units = n_msgs + (has_x ? 1 : 0);
+    const int n_slots = n_msgs < 3 ? 2 : 1;
+
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc(tmem_base_smem, 512);
+    const bool worker = tid < kWorkers;
+    if (P.weight_images != nullptr) {
+        // the images were built once for the whole layer (weight_images.cu): one coalesced copy
+        const uint4* __restrict__ src = reinterpret_cast<const uint4*>(P.weight_images);
+        uint4* dst = reinterpret_cast<uint4*>(base + FwdSmem16::kW1);
+        const int n16 = static_cast<int>((kWImg + n_msgs * 2 * kWImg) / 16);
+        for (int idx = tid; idx < n16; idx += kThreads) dst[idx] = __ldg(src + idx);
+    } else {
+    // weights: W1 as stored; per message W_k as stored and V_k = s_k W_k W1^T (thread t: row i = t/8, columns 8c..8c+7)
+    for (int idx = tid; idx < kC * 8; idx += kThreads) {
+        const int i = idx >> 3, ch = idx & 7;
+        const float4 a = __ldg(reinterpret_cast<const float4*>(P.att_w1 + i * kC) + ch * 2);
+        const float4 b = __ldg(reinterpret_cast<const float4*>(P.att_w1 + i * kC) + ch * 2 + 1);
+        const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        store_split8(base + FwdSmem16::kW1, kWPart, i, ch, v);
+    }
+    {
+        // V_k[i][h] = s_k sum_o W_k[i][o] W1[h][o].  Thread t keeps row h = t % 64 of W1 in registers and forms
+        // V_k[8 (t / 64) + e][h], e = 0..7 (the W_k rows are warp-uniform broadcast loads); the 64 x 64 result
+        // crosses to the image writers through a staging tile in the still idle operand slot 0.
+        const int h = tid & 63, ib = tid >> 6;
+        float w1row[kC];
+#pragma unroll
+        for (int o4 = 0; o4 < kC / 4; ++o4) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(P.att_w1 + h * kC) + o4);
+            w1row[4 * o4] = t.x; w1row[4 * o4 + 1] = t.y; w1row[4 * o4 + 2] = t.z; w1row[4 * o4 + 3] = t.w;
+        }
+        float* vs = reinterpret_cast<float*>(base + FwdSmem16::kA0);
+        for (int k = 0; k < n_msgs; ++k) {
+            uint8_t* w_img = base + FwdSmem16::kWV + k * 2 * kWImg;
+            uint8_t* v_img = w_img + kWImg;
+            const float sk = __ldg(P.scale[k]);
+            const float* __restrict__ wk = P.w[k];
+            if (worker) {
+                const int i = tid >> 3;
+                const float4 a = __ldg(reinterpret_cast<const float4*>(wk + i * kC) + c * 2);
+                const float4 b = __ldg(reinterpret_cast<const float4*>(wk + i * kC) + c * 2 + 1);
+                const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+                store_split8(w_img, kWPart, i, c, v);
+            }
+#pragma unroll 1
+            for (int e = 0; e < 8 && worker; ++e) {
+                const float4* __restrict__ wrow = reinterpret_cast<const float4*>(wk + (8 * ib + e) * kC);
+                float acc = 0.f;
+#pragma unroll
+                for (int o4 = 0; o4 < kC / 4; ++o4) {
+                    const float4 t = __ldg(wrow + o4);
+                    acc = fmaf(t.x, w1row[4 * o4], acc);
+                    acc = fmaf(t.y, w1row[4 * o4 + 1], acc);
+                    acc = fmaf(t.z, w1row[4 * o4 + 2], acc);
+                    acc = fmaf(t.w, w1row[4 * o4 + 3], acc);
+                }
+                vs[(8 * ib + e) * kC + h] = sk * acc;
+            }
+            __syncthreads();
+            if (worker) {
+                const int i = tid >> 3;
+                const float4 a = *reinterpret_cast<const float4*>(vs + i * kC + 8 * c);
+                const float4 b = *reinterpret_cast<const float4*>(vs + i * kC + 8 * c + 4);
+                const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+                store_split8(v_img, kWPart, i, c, v);
+            }
+            __syncthreads();
+        }
+    }
+    }   // images built in place
+    for (int i = tid; i < kC; i += kThreads) {
+        vecs[i] = __ldg(P.att_b1 + i);
+        vecs[kC + i] = __ldg(P.att_w2 + i);
+        vecs[2 * kC + i] = P.apply_ln ? __ldg(P.ln_gamma + i) : 1.f;
+        vecs[3 * kC + i] = P.apply_ln ? __ldg(P.ln_beta + i) : 0.f;
+    }
+    stamp(1);
+    fence_async_shared();
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    stamp(2);
+    const uint32_t tmem_base = *tmem_base_smem;
+    // tensor-memory columns: [D1 | H] x 2 buffers, then H0
+    const uint32_t tm_h0 = tmem_base + 256;
+    const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    const uint32_t slot_s[2] = {smem_u32(base + FwdSmem16::kA0), smem_u32(base + FwdSmem16::kA1)};
+    uint8_t* slot_p[2] = {base + FwdSmem16::kA0, base + FwdSmem16::kA1};
+    const uint32_t w1_s = smem_u32(base + FwdSmem16::kW1), wv_s = smem_u32(base + FwdSmem16::kWV);
+    const float b2 = __ldg(P.att_b2);
+    float scale_r[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) scale_r[k] = k < n_msgs ? __ldg(P.scale[k]) : 0.f;
+
+    if (!worker) {
+        // ================= MMA warp: waits for each staged unit, issues its product, commits to the slot's mbarrier =================
+        uint32_t unit_no = 0;
+        int slot = 0;
+        for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+#pragma unroll 1
+            for (int u = 0; u < n_units; ++u, ++unit_no) {
+                named_bar_sync(1 + (unit_no & 1u), kThreads);       // all 512 workers have staged unit u (and are past epilogue u - 2)
+                if (lane == 0) {
+                    tc_fence_after_sync();
+                    const int k = u - (has_x ? 1 : 0);
+                    if (dbg & 16) {
+                    } else if (k < 0) {
+                        gemm_bf16x3_unrolled<kC / 16>(tm_h0, k_major(slot_s[slot], kTileRows), k_major(w1_s, kC), idesc_bf16(128, 64, 0, 0), 0);
+                    } else {
+                        gemm_bf16x3_unrolled<kC / 16>(tmem_base + (k & 1) * 128, k_major(slot_s[slot], kTileRows),
+                                                      mn_major(wv_s + k * 2 * kWImg, kC, kWImg), idesc_bf16(128, 128, 0, 1), 0);
+                    }
+                    mma_commit(&bars[slot]);
+                }
+                __syncwarp();
+                slot = n_slots == 2 ? slot ^ 1 : 0;
+            }
+        }
+    } else {
+    // ================= workers =================
+    uint32_t par0 = 0u, par1 = 0u;
+    int pend0 = -1, pend1 = -1;     // unit whose MMAs are in flight on operand slot 0 / 1 (-1: none)
+    // wait until the MMAs that last read operand slot s (and wrote their accumulator) are complete
+    auto drain = [&](int s) {
+        if (s == 0) {
+            if (pend0 >= 0) { mbar_wait_backoff(&bars[0], par0); par0 ^= 1u; pend0 = -1; tc_fence_after_sync(); }
+        } else {
+            if (pend1 >= 0) { mbar_wait_backoff(&bars[1], par1); par1 ^= 1u; pend1 = -1; tc_fence_after_sync(); }
+        }
+    };
+    // source of unit u of a tile: x first (when present), then the aggregates
+    auto unit_src = [&](int u) -> const float* {
+        const int k = u - (has_x ? 1 : 0);
+        return k < 0 ? P.x : (k == 0 ? P.agg[0] : (k == 1 ? P.agg[1] : P.agg[2]));
+    };
+
+    float pf[2][8];                 // the next unit's rows, chunk map
+    {
+        const long long row0 = static_cast<long long>(blockIdx.x) * kTileRows;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) load_chunk(unit_src(0), row0 + ra + 64 * j, c, row0 + ra + 64 * j < live, pf[j]);
+    }
+    int slot = 0;                   // slot of the unit being staged (runs on across tiles)
+    uint32_t unit_no = 0;
+    float xn[kCW];                  // the next tile's residual slice
+    {
+        const long long nrow = static_cast<long long>(blockIdx.x) * kTileRows + r;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (has_x && nrow < live && !(dbg & 256)) t = ldg_pinned(reinterpret_cast<const float4*>(P.x + nrow * kC + col0) + j);
+            xn[4 * j] = t.x; xn[4 * j + 1] = t.y; xn[4 * j + 2] = t.z; xn[4 * j + 3] = t.w;
+        }
+    }
+    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const long long row0 = tile * kTileRows;
+        const long long row = row0 + r;
+        const bool row_alive = row < live;
+        float xr[kCW];              // row map: this thread's slice of the residual row (loaded one tile ahead)
+#pragma unroll
+        for (int i = 0; i < kCW; ++i) xr[i] = xn[i];
+        {
+            const long long nrow = (tile + gridDim.x) * kTileRows + r;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (has_x && nrow < live && !(dbg & 256)) t = ldg_pinned(reinterpret_cast<const float4*>(P.x + nrow * kC + col0) + j);
+                xn[4 * j] = t.x; xn[4 * j + 1] = t.y; xn[4 * j + 2] = t.z; xn[4 * j + 3] = t.w;
+            }
+        }
+        int prev_slot = 0;
+#pragma unroll 1
+        for (int u = 0; u <= n_units; ++u) {
+            if (u < n_units) {
+                // ---- stage unit u and hand it to the MMA warp (arrive, do not wait) ----
+                drain(slot);
+#pragma unroll
+                for (int j = 0; j < 2; ++j)
+                    if (!(dbg & 4)) store_split8(slot_p[slot], kPart, ra + 64 * j, c, pf[j]);
+                fence_async_shared();
+                tc_fence_before_sync();
+                named_bar_arrive(1 + (unit_no & 1u), kThreads);
+                ++unit_no;
+                if (slot == 0) pend0 = u; else pend1 = u;
+                // prefetch the next unit (of this tile, or the first one of this CTA's next tile)
+                {
+                    const bool wrap = u + 1 == n_units;
+                    const long long nrow0 = wrap ? (tile + gridDim.x) * kTileRows : row0;
+                    const float* __restrict__ src = unit_src(wrap ? 0 : u + 1);
+                    const bool any = !wrap || (tile + gridDim.x < tiles);
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) load_chunk(src, nrow0 + ra + 64 * j, c, !(dbg & 8) && any && (nrow0 + ra + 64 * j < live), pf[j]);
+                }
+            }
+            // ---- epilogue of unit u - 1 ----
+            if (u >= 1) {
+                const int k = u - 1 - (has_x ? 1 : 0);
+                if ((prev_slot == 0 ? pend0 : pend1) == u - 1) drain(prev_slot);   // (one slot: already drained before staging)
+                if (k >= 0) {
+                    const uint32_t tm = tmem_base + (k & 1) * 128 + lane_addr + col0;
+                    const float sk = k == 0 ? scale_r[0] : (k == 1 ? scale_r[1] : scale_r[2]);
+                    float m[kCW], h[kCW];
+                    if (!(dbg & 64)) {
+                        tmem_ld16(tm, m);
+                        tmem_ld16(tm + 64, h);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < kCW; ++i) m[i] = h[i] = 0.01f * i;
+                    }
+                    if (has_x && !(dbg & 64)) {
+                        float h0[kCW];
+                        tmem_ld16(tm_h0 + lane_addr + col0, h0);
+#pragma unroll
+                        for (int i = 0; i < kCW; ++i) h[i] += h0[i];
+                    }
+                    float part = 0.f;
+#pragma unroll
+                    for (int i = 0; i < kCW; ++i) {
+                        m[i] = fmaf(sk, m[i], xr[i]);                              // the message
+                        h[i] += vecs[col0 + i];                                    // pre-GELU hidden activation
+                        part = fmaf((dbg & 2) ? h[i] : gelu_fast_exact(h[i]), vecs[kC + col0 + i], part);
+                    }
+                    red[(k * 4 + q) * kTileRows + r] = part;
+                    float4* pm = reinterpret_cast<float4*>(P.saved_m[k]) + tf_index(row0, q, r);
+                    float4* pp = reinterpret_cast<float4*>(P.saved_pre[k]) + tf_index(row0, q, r);
+                    if (row_alive && !(dbg & 1)) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            pm[j * kTileRows] = make_float4(m[4 * j], m[4 * j + 1], m[4 * j + 2], m[4 * j + 3]);
+                            pp[j * kTileRows] = make_float4(h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]);
+                        }
+                    }
+                }
+                tc_fence_before_sync();
+            }
+            if (u < n_units) {
+                prev_slot = slot;
+                slot = n_slots == 2 ? slot ^ 1 : 0;
+            }
+        }
+        // ---------------- tile end: softmax over the messages, mix, LayerNorm ----------------
+        if (tile == blockIdx.x) stamp(3);
+        if (dbg & 128) continue;
+        named_bar_sync(3, kWorkers);                       // the partial scores are in `red`
+        float att[3];
+        {
+            float sc[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const float* rk = red + k * 4 * kTileRows;
+                sc[k] = k < n_msgs ? b2 + ((rk[r] + rk[kTileRows + r]) + (rk[2 * kTileRows + r] + rk[3 * kTileRows + r])) : 0.f;
+                if (k < n_msgs && q == 0 && row_alive) P.saved_score[k * rows + row] = sc[k];
+            }
+            float mx = sc[0];
+            if (n_msgs > 1) mx = fmaxf(mx, sc[1]);
+            if (n_msgs > 2) mx = fmaxf(mx, sc[2]);
+            const float e0 = expf(sc[0] - mx), e1 = n_msgs > 1 ? expf(sc[1] - mx) : 0.f, e2 = n_msgs > 2 ? expf(sc[2] - mx) : 0.f;
+            const float es = e0 + e1 + e2;
+            att[0] = e0 / es; att[1] = e1 / es; att[2] = e2 / es;
+        }
+        float y[kCW];
+#pragma unroll
+        for (int i = 0; i < kCW; ++i) y[i] = 0.f;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            if (k < n_msgs) {
+                // this thread wrote exactly these addresses a moment ago (same thread, program order)
+                const float4* pm = reinterpret_cast<const float4*>(P.saved_m[k]) + tf_index(row0, q, r);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float4 t = (row_alive && !(dbg & 32)) ? pm[j * kTileRows] : make_float4(0.f, 0.f, 0.f, 0.f);
+                    y[4 * j] = fmaf(att[k], t.x, y[4 * j]);
+                    y[4 * j + 1] = fmaf(att[k], t.y, y[4 * j + 1]);
+                    y[4 * j + 2] = fmaf(att[k], t.z, y[4 * j + 2]);
+                    y[4 * j + 3] = fmaf(att[k], t.w, y[4 * j + 3]);
+                }
+            }
+        }
+        if (P.apply_ln) {
+            float part = 0.f;
+#pragma unroll
+            for (int i = 0; i < kCW; ++i) part += y[i];
+            red[(3 * 4 + q) * kTileRows + r] = part;
+            named_bar_sync(3, kWorkers);
+            const float* rm = red + 3 * 4 * kTileRows;
+            const float mean = ((rm[r] + rm[kTileRows + r]) + (rm[2 * kTileRows + r] + rm[3 * kTileRows + r])) * (1.0f / kC);
+            float var = 0.f;
+#pragma unroll
+            for (int i = 0; i < kCW; ++i) var = fmaf(y[i] - mean, y[i] - mean, var);
+            red[q * kTileRows + r] = var;                  // slot 0: every thread is past its score reads
+            named_bar_sync(3, kWorkers);
+            const float rstd = 1.0f / sqrtf(((red[r] + red[kTileRows + r]) + (red[2 * kTileRows + r] + red[3 * kTileRows + r])) * (1.0f / kC) + P.ln_eps);
+#pragma unroll
+            for (int i = 0; i < kCW; ++i) y[i] = fmaf((y[i] - mean) * rstd, vecs[2 * kC + col0 + i], vecs[3 * kC + col0 + i]);
+        }
+        if (row_alive && !(dbg & 32)) {
+            float4* dst = reinterpret_cast<float4*>(out + row * kC + col0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) dst[j] = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
+        }
+        named_bar_sync(3, kWorkers);                       // `red` is rewritten by the next tile's epilogues
+        if (tile == blockIdx.x) stamp(4);
+    }
+    }   // workers
+    stamp(5);
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, 512);
+    stamp(6);
+}
+
+}  // namespace
+}  // namespace topo
+
+using namespace topo;
+
+static int g_fwd16_debug_mask = 0;
+// Differential-timing knob for scripts/ablate_fwd16.py (0 = the real kernel; results are WRONG for any other value).
+extern "C" void topo_debug_fwd16_mask(int mask) { g_fwd16_debug_mask = mask; }
+static unsigned long long* g_fwd16_stamps = nullptr;
+// globaltimer stamps of CTA 0 / thread 0 (7 x uint64): start, set-up done, after the set-up barrier, first tile's
+// unit loop done, first tile done, all tiles done, end
+extern "C" void topo_debug_fwd16_stamps(unsigned long long* device_buffer) { g_fwd16_stamps = device_buffer; }
+
+extern "C" int topo_sccn_combine_fwd_tc2(const topo_combine_params* p, int64_t rows, const int32_t* n_rows_dev,
+                                         float* out, topo_stream_t stream) {
+    TOPO_REQUIRE(p && out && rows >= 0, "bad argument");
+    TOPO_REQUIRE(p->n_msgs >= 1 && p->n_msgs <= 3, "n_msgs must be 1..3");
+    if (p->channels != kC) {
+        set_error("the tensor-core combine is instantiated for channels == 64");
+        return TOPO_ERR_UNSUPPORTED;
+    }
+    for (int k = 0; k < p->n_msgs; ++k)
+        TOPO_REQUIRE(p->agg[k] && p->w[k] && p->scale[k] && p->saved_m[k] && p->saved_pre[k],
+                     "null message operand (this kernel always saves m_k and pre_k)");
+    TOPO_REQUIRE(p->saved_score && p->saved_layout == TOPO_SAVED_TILE_FRAGMENT,
+                 "saved activations must be requested in the tile-fragment layout");
+    TOPO_REQUIRE(p->att_w1 && p->att_b1 && p->att_w2 && p->att_b2, "null attention parameter");
+    TOPO_REQUIRE(!p->apply_ln || (p->ln_gamma && p->ln_beta), "null LayerNorm parameter");
+    if (rows == 0) return TOPO_OK;
+    const size_t smem = FwdSmem16::kTotal;
+    if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(combine_fwd16_kernel), smem)) return rc;
+    const int tiles = static_cast<int>((rows + kTileRows - 1) / kTileRows);
+    combine_fwd16_kernel<<<std::min(tiles, sm_count()), kThreads, smem, as_stream(stream)>>>(*p, rows, n_rows_dev, out, g_fwd16_debug_mask, g_fwd16_stamps);
+    TOPO_LAUNCH_CHECK();
+    return TOPO_OK;
+}

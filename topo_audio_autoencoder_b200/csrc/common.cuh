@@ -91,6 +91,36 @@ __device__ __forceinline__ float gelu_exact_grad(float x) {
     return cdf + x * pdf;
 }
 
+// The same two functions without erff (about 20 instructions instead of 60, no divergent branch): for
+// z = |x| / sqrt 2,  erfc(z) = t P(t) exp(-z^2)  with  t = 1 / (1 + 0.42 z)  and P a degree-9 minimax fit of
+// erfcx(z) / t on z in [0, 10] (relative error 2.3e-9; fitted with scipy).  exp(-z^2) = exp(-x^2/2)
+// is also the Gaussian density the derivative needs.  Phi(x) = 1 - erfc(z)/2 for x >= 0 and erfc(z)/2 below, so
+// the negative tail keeps full relative accuracy (0.5 (1 + erf) cancels there).  In fp32: |gelu error| < 4e-7.
+__device__ __forceinline__ void gelu_cdf_pdf(float x, float& cdf, float& pdf) {
+    const float ax = fabsf(x);
+    float t;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(ax, 0.42f * 0.70710678118654752440f, 1.0f)));
+    float p = -0.04113744501622546f;
+    p = fmaf(p, t, 0.23070530236756076f);
+    p = fmaf(p, t, -0.4866430497963537f);
+    p = fmaf(p, t, 0.437150493790159f);
+    p = fmaf(p, t, -0.19732979111351331f);
+    p = fmaf(p, t, 0.2137338489469954f);
+    p = fmaf(p, t, 0.150040600633153f);
+    p = fmaf(p, t, 0.21989449846757936f);
+    p = fmaf(p, t, 0.23661221813005356f);
+    p = fmaf(p, t, 0.23697332130814744f);
+    const float e = __expf(-0.5f * x * x);
+    const float hq = 0.5f * t * p * e;                 // erfc(|x| / sqrt 2) / 2 = Phi(-|x|)
+    cdf = x >= 0.0f ? 1.0f - hq : hq;
+    pdf = 0.39894228040143267794f * e;
+}
+__device__ __forceinline__ float gelu_fast_exact(float x) {
+    float cdf, pdf;
+    gelu_cdf_pdf(x, cdf, pdf);
+    return x * cdf;
+}
+
 template <int VEC>
 struct Vec;
 template <>

@@ -1,0 +1,90 @@
+// Operand images of the SCCN weights for the bf16x3 tensor-core kernels, built ONCE per layer and step.
+//
+// Every CTA of the combine kernels needs its rank's weights as bf16x3 SWIZZLE_128B images (tc16.cuh), plus, for
+// the forward, the folded matrices V_k = s_k W_k W1^T.  Building them inside the kernels cost ~30 us of serial
+// load latency per launch (48 launches per step).  This kernel writes them to global memory in exactly the byte
+// layout the kernels keep in shared memory, so a CTA's set-up is one coalesced copy.
+//   job with w:    dst = [ W_k image (24 KB) | V_k image (24 KB) ]
+//   job without w: dst = [ W1 image (24 KB) ]
+#include "common.cuh"
+#include "tc16.cuh"
+
+namespace topo {
+namespace {
+
+using namespace tc16;
+
+constexpr int kC = 64;
+constexpr uint32_t kWPart = kC * 128;
+constexpr uint32_t kWImg = 3 * kWPart;
+constexpr int kMaxJobs = 16;
+
+struct ImageJobs {
+    topo_image_job j[kMaxJobs];
+};
+
+__global__ void __launch_bounds__(512) prepare_images_kernel(const __grid_constant__ ImageJobs jobs) {
+    __shared__ __align__(16) float w1s[kC][kC + 4];    // W1 [o][i], padded rows (bank-conflict-free column walks)
+    __shared__ __align__(16) float wks[kC][kC + 4];    // W_k [in][out]
+    const topo_image_job job = jobs.j[blockIdx.x];
+    uint8_t* dst = static_cast<uint8_t*>(job.dst);
+    const int tid = threadIdx.x, i = tid >> 3, c = tid & 7;
+    // coalesced loads of both matrices (eight lanes = one 256-byte row)
+    {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(job.att_w1 + i * kC) + c * 2);
+        const float4 b = __ldg(reinterpret_cast<const float4*>(job.att_w1 + i * kC) + c * 2 + 1);
+        *reinterpret_cast<float4*>(&w1s[i][8 * c]) = a;
+        *reinterpret_cast<float4*>(&w1s[i][8 * c + 4]) = b;
+        if (job.w == nullptr) {
+            const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+            store_split8(dst, kWPart, i, c, v);
+            return;
+        }
+    }
+    const float4 a = __ldg(reinterpret_cast<const float4*>(job.w + i * kC) + c * 2);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(job.w + i * kC) + c * 2 + 1);
+    *reinterpret_cast<float4*>(&wks[i][8 * c]) = a;
+    *reinterpret_cast<float4*>(&wks[i][8 * c + 4]) = b;
+    {
+        const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        store_split8(dst, kWPart, i, c, v);
+    }
+    const float sk = __ldg(job.scale);
+    __syncthreads();
+    // V[i][h] = s sum_o W_k[i][o] W1[h][o], h = 8c .. 8c+7
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+#pragma unroll 4
+    for (int o = 0; o < kC; ++o) {
+        const float w = wks[i][o];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = fmaf(w, w1s[8 * c + e][o], acc[e]);
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] *= sk;
+    store_split8(dst + kWImg, kWPart, i, c, acc);
+}
+
+}  // namespace
+}  // namespace topo
+
+using namespace topo;
+
+extern "C" int topo_sccn_prepare_images(const topo_image_job* jobs, int n_jobs, int channels, topo_stream_t stream) {
+    TOPO_REQUIRE(jobs && n_jobs >= 0 && n_jobs <= kMaxJobs, "1..16 jobs per call");
+    if (channels != kC) {
+        set_error("weight images exist for channels == 64 (the tensor-core kernels)");
+        return TOPO_ERR_UNSUPPORTED;
+    }
+    if (n_jobs == 0) return TOPO_OK;
+    ImageJobs packed{};
+    for (int q = 0; q < n_jobs; ++q) {
+        TOPO_REQUIRE(jobs[q].att_w1 && jobs[q].dst && (jobs[q].w == nullptr || jobs[q].scale), "null pointer in an image job");
+        TOPO_REQUIRE((reinterpret_cast<uintptr_t>(jobs[q].dst) & 15u) == 0, "image destinations must be 16-byte aligned");
+        packed.j[q] = jobs[q];
+    }
+    prepare_images_kernel<<<n_jobs, 512, 0, as_stream(stream)>>>(packed);
+    TOPO_LAUNCH_CHECK();
+    return TOPO_OK;
+}

@@ -25,7 +25,8 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from ._lib import lib, check, ptr, ptr_array, stream, ComplexView, CombineParams, CombineGrads
+from ._lib import (lib, check, ptr, ptr_array, stream, ComplexView, CombineParams, CombineGrads, ImageJob,
+                   WEIGHT_IMAGE_BYTES)
 from .rectifier import _Tables
 
 
@@ -95,13 +96,19 @@ SAVE_ACTIVATIONS = True
 # with the tensor-core forward's saved activations, run the whole combine backward as ONE bf16x3 tensor-core
 # kernel (csrc/combine_bwd_tc.cu) instead of the FFMA attention kernel + the 3xTF32 conv kernel
 FUSED_BACKWARD = True
+# tensor-core forward generation: 1 = 3xTF32, two chained GEMMs per message (csrc/combine_tc.cu);
+# 2 = bf16x3, one 128 x 128 x 64 product per message, double-buffered, tile-fragment saves (csrc/combine_fwd16.cu)
+FORWARD_TC_GENERATION = 2
+# build the weights' operand images once per layer and step (one small launch) instead of inside every
+# tensor-core kernel launch
+SHARED_WEIGHT_IMAGES = True
 
 
 class _CombineFn(torch.autograd.Function):
     """out = [LayerNorm] sum_k softmax_k(att(m_k)) m_k,  m_k = scale_k (agg_k @ W_k) + x."""
 
     @staticmethod
-    def forward(ctx, n_msgs, apply_ln, ln_eps, n_rows_dev, zero_dead_rows, x, att_w1, att_b1, att_w2, att_b2, ln_g, ln_b, *rest):
+    def forward(ctx, n_msgs, apply_ln, ln_eps, n_rows_dev, zero_dead_rows, images, x, att_w1, att_b1, att_w2, att_b2, ln_g, ln_b, *rest):
         aggs = [t.contiguous() for t in rest[:n_msgs]]
         ws = [t.contiguous() for t in rest[n_msgs:2 * n_msgs]]
         scales = [t.contiguous() for t in rest[2 * n_msgs:3 * n_msgs]]
@@ -111,26 +118,30 @@ class _CombineFn(torch.autograd.Function):
                    ln_g.contiguous(), ln_b.contiguous()]
         dev = aggs[0].device
         saved = None
+        use_tc = COMBINE_IMPL == "tc" and ch == 64
+        tile_fragment = False
         if SAVE_ACTIVATIONS and any(ctx.needs_input_grad):
             # the messages and the pre-GELU attention layer, kept for the backward (skips both recompute GEMMs)
-            saved = ([torch.empty(rows, ch, dtype=torch.float32, device=dev) for _ in range(n_msgs)],
-                     [torch.empty(rows, ch, dtype=torch.float32, device=dev) for _ in range(n_msgs)],
+            tile_fragment = use_tc and FORWARD_TC_GENERATION == 2
+            rows_alloc = -(-rows // 128) * 128 if tile_fragment else rows     # the tile-fragment layout permutes inside 128-row tiles
+            saved = ([torch.empty(rows_alloc, ch, dtype=torch.float32, device=dev) for _ in range(n_msgs)],
+                     [torch.empty(rows_alloc, ch, dtype=torch.float32, device=dev) for _ in range(n_msgs)],
                      torch.empty(3, rows, dtype=torch.float32, device=dev))      # attention scores (tensor-core forward)
-        params = _make_params(ch, n_msgs, aggs, ws, scales, x_c, tensors, ln_eps, apply_ln, saved)
+        params = _make_params(ch, n_msgs, aggs, ws, scales, x_c, tensors, ln_eps, apply_ln, saved, tile_fragment, images)
         # rows past the live count are never read by any kernel; they are zero-filled only where the tensor is
         # handed to the caller (last layer), so that padded buffers are safe to reduce over
         out = (torch.zeros if zero_dead_rows else torch.empty)(rows, ch, dtype=torch.float32, device=dev)
-        use_tc = COMBINE_IMPL == "tc" and ch == 64
-        fwd = lib.topo_sccn_combine_fwd_tc if use_tc else lib.topo_sccn_combine_fwd
+        fwd = (lib.topo_sccn_combine_fwd_tc2 if tile_fragment else lib.topo_sccn_combine_fwd_tc) if use_tc else lib.topo_sccn_combine_fwd
         check(fwd(C.byref(params), rows, ptr(n_rows_dev, torch.int32), ptr(out), stream()))
         ctx.save_for_backward(x_c, n_rows_dev, *tensors, *aggs, *ws, *scales)
         ctx.saved_act = saved
-        ctx.cfg = (n_msgs, bool(apply_ln), float(ln_eps), x is not None, use_tc and saved is not None)
+        ctx.images = images
+        ctx.cfg = (n_msgs, bool(apply_ln), float(ln_eps), x is not None, use_tc and saved is not None, tile_fragment)
         return out
 
     @staticmethod
     def backward(ctx, g_out):
-        n_msgs, apply_ln, ln_eps, has_x, fused = ctx.cfg
+        n_msgs, apply_ln, ln_eps, has_x, fused, tile_fragment = ctx.cfg
         saved = ctx.saved_tensors
         x_c, n_rows_dev, tensors = saved[0], saved[1], list(saved[2:8])
         aggs = list(saved[8:8 + n_msgs])
@@ -138,7 +149,7 @@ class _CombineFn(torch.autograd.Function):
         scales = list(saved[8 + 2 * n_msgs:8 + 3 * n_msgs])
         rows, ch = aggs[0].shape
         dev = aggs[0].device
-        params = _make_params(ch, n_msgs, aggs, ws, scales, x_c, tensors, ln_eps, apply_ln, ctx.saved_act)
+        params = _make_params(ch, n_msgs, aggs, ws, scales, x_c, tensors, ln_eps, apply_ln, ctx.saved_act, tile_fragment, ctx.images)
         g_aggs = [torch.empty(rows, ch, dtype=torch.float32, device=dev) for _ in range(n_msgs)]
         g_x = torch.empty(rows, ch, dtype=torch.float32, device=dev) if has_x else None
         wprod = [torch.zeros(ch, ch, dtype=torch.float32, device=dev) for _ in range(n_msgs)]
@@ -154,7 +165,7 @@ class _CombineFn(torch.autograd.Function):
         grads.g_att_w2, grads.g_att_b2 = ptr(g_w2), ptr(g_b2)
         grads.g_ln_gamma, grads.g_ln_beta = ptr(g_g), ptr(g_b)
         g_out = g_out.contiguous()     # named: a temporary would be freed before the launch reads it
-        if fused and FUSED_BACKWARD:
+        if fused and (FUSED_BACKWARD or tile_fragment):     # the FFMA kernels read row-major saves only
             # one tensor-core kernel: attention / LayerNorm backward, input gradients and weight-gradient products
             check(lib.topo_sccn_combine_bwd_tc(C.byref(params), rows, ptr(n_rows_dev, torch.int32), ptr(g_out),
                                                C.byref(grads), stream()))
@@ -167,11 +178,12 @@ class _CombineFn(torch.autograd.Function):
         # finish the conv-weight chain: dW_k = scale_k P_k,  dscale_k = <W_k, P_k>
         g_ws = [wprod[k] * scales[k] for k in range(n_msgs)]
         g_ss = [(wprod[k] * ws[k]).sum().reshape(scales[k].shape) for k in range(n_msgs)]
-        return (None, None, None, None, None, g_x, g_w1, g_b1, g_w2, g_b2,
+        return (None, None, None, None, None, None, g_x, g_w1, g_b1, g_w2, g_b2,
                 g_g if apply_ln else None, g_b if apply_ln else None, *g_aggs, *g_ws, *g_ss)
 
 
-def _make_params(ch, n_msgs, aggs, ws, scales, x, tensors, ln_eps, apply_ln, saved=None) -> CombineParams:
+def _make_params(ch, n_msgs, aggs, ws, scales, x, tensors, ln_eps, apply_ln, saved=None, tile_fragment=False,
+                 images: Optional[torch.Tensor] = None) -> CombineParams:
     p = CombineParams()
     p.channels, p.n_msgs = ch, n_msgs
     for k in range(3):
@@ -181,6 +193,8 @@ def _make_params(ch, n_msgs, aggs, ws, scales, x, tensors, ln_eps, apply_ln, sav
         p.saved_m[k] = ptr(saved[0][k]) if (saved is not None and k < n_msgs) else None
         p.saved_pre[k] = ptr(saved[1][k]) if (saved is not None and k < n_msgs) else None
     p.saved_score = ptr(saved[2]) if (saved is not None and len(saved) > 2) else None
+    p.saved_layout = 1 if tile_fragment else 0       # TOPO_SAVED_TILE_FRAGMENT / TOPO_SAVED_ROW_MAJOR
+    p.weight_images = ptr(images, torch.uint8) if images is not None else None
     p.x = ptr(x)
     p.att_w1, p.att_b1, p.att_w2, p.att_b2 = (ptr(t) for t in tensors[:4])
     p.ln_gamma, p.ln_beta = ptr(tensors[4]), ptr(tensors[5])
@@ -311,11 +325,12 @@ class GradientSCCNLayer(nn.Module):
 
     # -- shared tail: messages -> output rows --------------------------------------------------
     def _combine(self, key: str, x: torch.Tensor, msgs: Sequence[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]],
-                 n_rows_dev: Optional[torch.Tensor] = None, zero_dead_rows: bool = True) -> torch.Tensor:
+                 n_rows_dev: Optional[torch.Tensor] = None, zero_dead_rows: bool = True,
+                 images: Optional[torch.Tensor] = None) -> torch.Tensor:
         att, ln = self.message_attention[key], self.layer_norms[key]
         apply_ln = self.training and not self.is_final_layer                                               # :133-134
         aggs, ws, scales = zip(*msgs)
-        return _CombineFn.apply(len(msgs), apply_ln, ln.eps, n_rows_dev, zero_dead_rows, x if self.residual else None,
+        return _CombineFn.apply(len(msgs), apply_ln, ln.eps, n_rows_dev, zero_dead_rows, images, x if self.residual else None,
                                 att[0].weight, att[0].bias, att[2].weight.reshape(-1), att[2].bias,
                                 ln.weight, ln.bias, *aggs, *ws, *scales)
 
@@ -366,7 +381,7 @@ class GradientSCCNLayer(nn.Module):
         d0, d1, d2, u1, u2, u3, s0, s1, s2, s3 = _AggregateFn.apply(cx, cx.probs, *xs)
         same, down, up = (s0, s1, s2, s3), (d0, d1, d2, None), (None, u1, u2, u3)
         sc = self.message_scales
-        out = []
+        per_rank = []
         for r in range(4):
             key = f"rank_{r}"
             msgs = [(same[r], self.convs_same_rank[key].weight, sc["same_rank"])]
@@ -374,8 +389,34 @@ class GradientSCCNLayer(nn.Module):
                 msgs.append((down[r], self.convs_high_to_low[key].weight, sc["high_to_low"]))
             if r > 0:
                 msgs.append((up[r], self.convs_low_to_high[key].weight, sc["low_to_high"]))
-            out.append(self._combine(key, xs[r], msgs, cx.live_rows(r), zero_dead_rows) if cx.rows_max[r] else xs[r])
+            per_rank.append((key, msgs))
+        images = self._weight_images(per_rank, xs[0].device) if (COMBINE_IMPL == "tc" and self.channels == 64 and SHARED_WEIGHT_IMAGES) else [None] * 4
+        out = []
+        for r, (key, msgs) in enumerate(per_rank):
+            out.append(self._combine(key, xs[r], msgs, cx.live_rows(r), zero_dead_rows, images[r]) if cx.rows_max[r] else xs[r])
         return out
+
+    def _weight_images(self, per_rank, device) -> List[torch.Tensor]:
+        """bf16x3 operand images of this layer's weights for all ranks, built by ONE launch (csrc/weight_images.cu)
+        and shared by the forward and backward tensor-core kernels: per rank [W1 | k: W_k, V_k = s_k W_k W1^T]."""
+        sizes = [WEIGHT_IMAGE_BYTES * (1 + 2 * len(msgs)) for _, msgs in per_rank]
+        buf = torch.empty(sum(sizes), dtype=torch.uint8, device=device)
+        views, jobs, off = [], [], 0
+        for (key, msgs), size in zip(per_rank, sizes):
+            views.append(buf[off:off + size])
+            w1 = self.message_attention[key][0].weight.detach().contiguous()
+            base = buf.data_ptr() + off
+            jobs.append((None, None, w1, base))
+            for k, (_, w, s) in enumerate(msgs):
+                jobs.append((w.detach().contiguous(), s.detach().contiguous(), w1, base + WEIGHT_IMAGE_BYTES * (1 + 2 * k)))
+            off += size
+        arr = (ImageJob * len(jobs))()
+        keep = []
+        for q, (w, s, w1, dst) in enumerate(jobs):
+            arr[q].w, arr[q].scale, arr[q].att_w1, arr[q].dst = ptr(w), ptr(s), ptr(w1), dst
+            keep.append((w, s, w1))
+        check(lib.topo_sccn_prepare_images(arr, len(jobs), self.channels, stream()))
+        return views
 
 
 class GradientSCCN(nn.Module):
