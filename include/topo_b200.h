@@ -249,6 +249,10 @@ typedef struct {
      *   [ W1 image | message 0: W image, V image | message 1: ... ]   (24 KB each)
      * When NULL the tensor-core kernels build the images themselves (about 30 us of set-up per launch). */
     const void* weight_images;
+    /* Upper bound on the CTAs (= SMs) the tensor-core kernels of this call may occupy; 0 = all of them.  The four
+     * ranks of a layer are independent, so the host launches them on four streams with the SMs divided in
+     * proportion to their work: they run side by side instead of paying four set-ups and four tails in turn. */
+    int max_ctas;
 } topo_combine_params;
 
 #define TOPO_SAVED_ROW_MAJOR 0
@@ -279,6 +283,17 @@ typedef struct {
 } topo_image_job;
 #define TOPO_WEIGHT_IMAGE_BYTES 24576
 int topo_sccn_prepare_images(const topo_image_job* jobs, int n_jobs, int channels, topo_stream_t stream);
+
+/* The tail of the conv-weight chain for up to 16 messages in one launch (one CTA each, deterministic):
+ *   g_w = scale * wprod   ([C, C]),   g_scale[0] = <w, wprod>      with wprod = g_wprod of topo_combine_grads. */
+typedef struct {
+    const float* wprod;
+    const float* w;
+    const float* scale;
+    float* g_w;
+    float* g_scale;
+} topo_wgrad_job;
+int topo_sccn_finish_weight_grads(const topo_wgrad_job* jobs, int n_jobs, int channels, topo_stream_t stream);
 
 int topo_sccn_combine_fwd(const topo_combine_params* p, int64_t rows, const int32_t* n_rows_dev,
                           float* out, topo_stream_t stream);

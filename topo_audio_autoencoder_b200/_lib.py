@@ -35,7 +35,7 @@ class CombineParams(C.Structure):
                 ("att_w2", C.c_void_p), ("att_b2", C.c_void_p),
                 ("ln_gamma", C.c_void_p), ("ln_beta", C.c_void_p),
                 ("ln_eps", C.c_float), ("apply_ln", C.c_int),
-                ("saved_m", C.c_void_p * 3), ("saved_pre", C.c_void_p * 3), ("saved_score", C.c_void_p), ("saved_layout", C.c_int), ("weight_images", C.c_void_p)]
+                ("saved_m", C.c_void_p * 3), ("saved_pre", C.c_void_p * 3), ("saved_score", C.c_void_p), ("saved_layout", C.c_int), ("weight_images", C.c_void_p), ("max_ctas", C.c_int)]
 
 
 class ImageJob(C.Structure):
@@ -44,6 +44,11 @@ class ImageJob(C.Structure):
 
 
 WEIGHT_IMAGE_BYTES = 24576
+
+
+class WgradJob(C.Structure):
+    """topo_wgrad_job"""
+    _fields_ = [("wprod", C.c_void_p), ("w", C.c_void_p), ("scale", C.c_void_p), ("g_w", C.c_void_p), ("g_scale", C.c_void_p)]
 
 
 class CombineGrads(C.Structure):
@@ -89,6 +94,7 @@ SIGNATURES = {
     "topo_spmm_csr": [_I64, _P, _P, _P, _P, _I32, _P, _P],
     "topo_sddmm_csr": [_I64, _P, _P, _P, _P, _I32, _P, _P],
     "topo_sccn_prepare_images": [C.POINTER(ImageJob), _I32, _I32, _P],
+    "topo_sccn_finish_weight_grads": [C.POINTER(WgradJob), _I32, _I32, _P],
     "topo_sccn_combine_fwd": [C.POINTER(CombineParams), _I64, _P, _P, _P],
     "topo_sccn_combine_fwd_tc": [C.POINTER(CombineParams), _I64, _P, _P, _P],
     "topo_sccn_combine_fwd_tc2": [C.POINTER(CombineParams), _I64, _P, _P, _P],
@@ -127,7 +133,7 @@ KERNELS_PER_CALL = {
     "topo_active_sets": 2, "topo_penalties_fwd": 1, "topo_penalties_bwd": 1, "topo_embed_fwd": 1,
     "topo_embed_bwd": 2, "topo_layernorm_fwd": 1, "topo_layernorm_bwd": 1, "topo_operators_count": 2,
     "topo_operators_fill": 1, "topo_operators_bwd": 1, "topo_sccn_aggregate_fwd": 2, "topo_sccn_aggregate_bwd": 2,
-    "topo_spmm_csr": 1, "topo_sddmm_csr": 1, "topo_sccn_prepare_images": 1, "topo_sccn_combine_fwd": 1, "topo_sccn_combine_fwd_tc": 1, "topo_sccn_combine_fwd_tc2": 1, "topo_sccn_combine_bwd": 2,
+    "topo_spmm_csr": 1, "topo_sddmm_csr": 1, "topo_sccn_prepare_images": 1, "topo_sccn_finish_weight_grads": 1, "topo_sccn_combine_fwd": 1, "topo_sccn_combine_fwd_tc": 1, "topo_sccn_combine_fwd_tc2": 1, "topo_sccn_combine_bwd": 2,
     "topo_sccn_combine_bwd_attention": 1, "topo_sccn_combine_bwd_conv": 1, "topo_sccn_combine_bwd_conv_tc": 1, "topo_sccn_combine_bwd_tc": 1, "topo_distance_prepare": 1,
     "topo_distance_rows": 1, "topo_debug_gemm_tf32x3": 1, "topo_debug_gemm_bf16x3": 1,
 }

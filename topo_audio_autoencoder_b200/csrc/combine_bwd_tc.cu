@@ -99,6 +99,18 @@ __device__ __forceinline__ float row_sum8(float v) {
     return v;
 }
 
+// the same for two values at once (independent shuffles interleave)
+__device__ __forceinline__ void row_sum8_pair(float& a, float& b) {
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+        const float ta = __shfl_xor_sync(0xffffffffu, a, o), tb = __shfl_xor_sync(0xffffffffu, b, o);
+        a += ta;
+        b += tb;
+    }
+}
+
+__device__ __forceinline__ void prefetch_l2_line(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 __device__ __forceinline__ uint32_t dy_off(int row, int c16 /* 0..15 */) {
     return static_cast<uint32_t>(row * 256 + ((c16 ^ (row & 7)) << 4));
 }
@@ -119,10 +131,22 @@ __device__ __forceinline__ void stage_weight16(const float* __restrict__ w, uint
 //              the column sums accumulate in registers.  All element-wise work runs in this mapping.
 //   row map:   thread (q, r) = (t / 128, t % 128) owns columns [16 q, 16 q + 16) of row r = TMEM lane r.  Only
 //              the two tensor-memory epilogues use it; dy and the softmax weights cross over in shared memory.
+template <int NM>
 __global__ void __launch_bounds__(kThreads, 1) combine_bwd_fused_kernel(topo_combine_params P, long long rows,
                                                                         const int* __restrict__ n_rows_dev,
                                                                         const float* __restrict__ grad_out,
-                                                                        topo_combine_grads G) {
+                                                                        topo_combine_grads G,
+                                                                        unsigned long long* __restrict__ stamps) {
+    int stamp_no = 0;
+    auto stamp = [&]() {
+        if (stamps != nullptr && blockIdx.x == 0 && threadIdx.x == 0 && stamp_no < 62) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            stamps[stamp_no] = t;
+        }
+        ++stamp_no;
+    };
+    stamp();                                                   // 0: kernel start
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* base = smem_raw;
     uint8_t* q_img = base + BwdSmem::kQ;
@@ -140,12 +164,12 @@ __global__ void __launch_bounds__(kThreads, 1) combine_bwd_fused_kernel(topo_com
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int q = tid >> 7, r = tid & 127, col0 = q * kCW;     // row map
     const int c = tid & 7, ra = tid >> 3;                       // chunk map: rows ra and ra + 64
-    const int n_msgs = P.n_msgs;
+    constexpr int n_msgs = NM;
     const bool apply_ln = P.apply_ln != 0;
     const bool tf = P.saved_layout == TOPO_SAVED_TILE_FRAGMENT;
 
     if (tid == 0) {
-        mbar_init(bar, 1);
+        mbar_init(bar, 3);            // three issuing threads commit every round
         fence_barrier_init();
     }
     if (warp == 0) tmem_alloc(tmem_base_smem, 512);
@@ -176,6 +200,16 @@ __global__ void __launch_bounds__(kThreads, 1) combine_bwd_fused_kernel(topo_com
     // tensor-memory columns: T | Ga | DW1 | DWp_0 | DWp_1 | DWp_2
     const uint32_t tm_t = tmem_base, tm_ga = tmem_base + 64, tm_dw1 = tmem_base + 128, tm_dwp = tmem_base + 192;
     const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    {
+        // DW1 / DWp start at zero: every weight-gradient MMA accumulates, whoever issues it first
+        const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int c8 = 0; c8 < 8; ++c8) tmem_st8(tm_dw1 + lane_addr + q * 64 + c8 * 8, z);
+        tmem_st_wait();
+        tc_fence_before_sync();
+        __syncthreads();
+        tc_fence_after_sync();
+    }
     const uint32_t p_s = smem_u32(p_img), q_s = smem_u32(q_img);
     const uint32_t w1_s = smem_u32(base + BwdSmem::kW1), wk_s = smem_u32(base + BwdSmem::kWk);
     float scale_r[3];
@@ -193,12 +227,17 @@ __global__ void __launch_bounds__(kThreads, 1) combine_bwd_fused_kernel(topo_com
         const long long row0 = tile * kTileRows;
         const long long grow[2] = {row0 + ra, row0 + ra + 64};
         const bool alive[2] = {grow[0] < live, grow[1] < live};
+        stamp();                                               // tile start
         // ---------------- phase A (chunk map): softmax weights, LayerNorm backward, dscore ----------------
+        // Both rows of the thread advance together (every statement is written for j = 0, 1) so that their
+        // dependent chains -- loads, row reductions, exp, rsqrt -- overlap instead of running back to back.
         float dy[2][8], dsc[2][3];
         {
-            float mk[3][2][8], att[2][3];
+            float mk[3][2][8], att[2][3], sc[2][3];
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) sc[j][k] = (k < n_msgs && alive[j]) ? __ldg(P.saved_score + k * rows + grow[j]) : 0.f;
                 load_chunk(grad_out, grow[j], c, alive[j], dy[j]);
 #pragma unroll
                 for (int k = 0; k < 3; ++k)
@@ -206,68 +245,91 @@ __global__ void __launch_bounds__(kThreads, 1) combine_bwd_fused_kernel(topo_com
             }
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
-                float sc[3];
-#pragma unroll
-                for (int k = 0; k < 3; ++k) sc[k] = (k < n_msgs && alive[j]) ? __ldg(P.saved_score + k * rows + grow[j]) : 0.f;
-                float mx = sc[0];
-                if (n_msgs > 1) mx = fmaxf(mx, sc[1]);
-                if (n_msgs > 2) mx = fmaxf(mx, sc[2]);
-                const float e0 = expf(sc[0] - mx), e1 = n_msgs > 1 ? expf(sc[1] - mx) : 0.f, e2 = n_msgs > 2 ? expf(sc[2] - mx) : 0.f;
-                const float es = e0 + e1 + e2;
-                att[j][0] = e0 / es; att[j][1] = e1 / es; att[j][2] = e2 / es;
+                float mx = sc[j][0];
+                if (n_msgs > 1) mx = fmaxf(mx, sc[j][1]);
+                if (n_msgs > 2) mx = fmaxf(mx, sc[j][2]);
+                const float e0 = expf(sc[j][0] - mx), e1 = n_msgs > 1 ? expf(sc[j][1] - mx) : 0.f, e2 = n_msgs > 2 ? expf(sc[j][2] - mx) : 0.f;
+                const float inv = 1.0f / (e0 + e1 + e2);
+                att[j][0] = e0 * inv; att[j][1] = e1 * inv; att[j][2] = e2 * inv;
                 if (c == 0) {
 #pragma unroll
                     for (int k = 0; k < 3; ++k) att_s[k * kTileRows + ra + 64 * j] = att[j][k];
                 }
-                if (apply_ln) {
-                    float y[8];
+            }
+            stamp();                                           // scores arrived, softmax done
+            if (apply_ln) {
+                float y[2][8], s0[2], mean[2], rstd[2], c1[2], c2[2];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) y[i] = 0.f;
+                for (int j = 0; j < 2; ++j) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) y[j][i] = 0.f;
 #pragma unroll
                     for (int k = 0; k < 3; ++k) {
                         if (k < n_msgs) {
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) y[i] = fmaf(att[j][k], mk[k][j][i], y[i]);
+                            for (int i = 0; i < 8; ++i) y[j][i] = fmaf(att[j][k], mk[k][j][i], y[j][i]);
                         }
                     }
-                    float part = 0.f;
+                    s0[j] = 0.f;
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) part += y[i];
-                    const float mean = row_sum8(part) * (1.0f / kC);
-                    float var = 0.f;
+                    for (int i = 0; i < 8; ++i) s0[j] += y[j][i];
+                }
+                row_sum8_pair(s0[0], s0[1]);
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) var = fmaf(y[i] - mean, y[i] - mean, var);
-                    const float rstd = 1.0f / sqrtf(row_sum8(var) * (1.0f / kC) + P.ln_eps);
-                    float c1 = 0.f, c2 = 0.f;
+                for (int j = 0; j < 2; ++j) {
+                    mean[j] = s0[j] * (1.0f / kC);
+                    s0[j] = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) s0[j] = fmaf(y[j][i] - mean[j], y[j][i] - mean[j], s0[j]);
+                }
+                row_sum8_pair(s0[0], s0[1]);
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    rstd[j] = 1.0f / sqrtf(s0[j] * (1.0f / kC) + P.ln_eps);
+                    c1[j] = c2[j] = 0.f;
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
-                        y[i] = (y[i] - mean) * rstd;                          // x-hat
-                        p_gamma[i] = fmaf(dy[j][i], y[i], p_gamma[i]);
+                        y[j][i] = (y[j][i] - mean[j]) * rstd[j];              // x-hat
+                        p_gamma[i] = fmaf(dy[j][i], y[j][i], p_gamma[i]);
                         p_beta[i] += dy[j][i];
                         const float gy = dy[j][i] * gmc[i];
-                        c1 += gy;
-                        c2 = fmaf(gy, y[i], c2);
+                        c1[j] += gy;
+                        c2[j] = fmaf(gy, y[j][i], c2[j]);
                     }
-                    c1 = row_sum8(c1) * (1.0f / kC);
-                    c2 = row_sum8(c2) * (1.0f / kC);
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) dy[j][i] = rstd * (dy[j][i] * gmc[i] - c1 - y[i] * c2);
                 }
-                // dscore_k = a_k (dy . m_k - sum_j a_j dy . m_j)
-                float da[3], dot = 0.f;
+                row_sum8_pair(c1[0], c1[1]);
+                row_sum8_pair(c2[0], c2[1]);
 #pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    float part = 0.f;
+                for (int j = 0; j < 2; ++j) {
+                    c1[j] *= (1.0f / kC);
+                    c2[j] *= (1.0f / kC);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) dy[j][i] = rstd[j] * (dy[j][i] * gmc[i] - c1[j] - y[j][i] * c2[j]);
+                }
+            }
+            // dscore_k = a_k (dy . m_k - sum_j a_j dy . m_j)
+            float da[2][3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    da[j][k] = 0.f;
                     if (k < n_msgs) {
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) part = fmaf(dy[j][i], mk[k][j][i], part);
+                        for (int i = 0; i < 8; ++i) da[j][k] = fmaf(dy[j][i], mk[k][j][i], da[j][k]);
                     }
-                    da[k] = row_sum8(part);
-                    dot = fmaf(att[j][k], da[k], dot);
                 }
+                if (k < n_msgs) row_sum8_pair(da[0][k], da[1][k]);
+            }
+            stamp();                                           // LayerNorm backward + dscore done
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                float dot = 0.f;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) dot = fmaf(att[j][k], da[j][k], dot);
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
-                    dsc[j][k] = (k < n_msgs && alive[j]) ? att[j][k] * (da[k] - dot) : 0.f;
+                    dsc[j][k] = (k < n_msgs && alive[j]) ? att[j][k] * (da[j][k] - dot) : 0.f;
                     if (c == 0) p_b2 += dsc[j][k];
                 }
                 // dy crosses to the row map through shared memory.  Lanes 0..3 of a row store their first 16-byte
@@ -282,7 +344,22 @@ __global__ void __launch_bounds__(kThreads, 1) combine_bwd_fused_kernel(topo_com
                 store_split8(q_img, kPart, rr, c, mk[0][j]);
             }
         }
-
+        if (tile + gridDim.x < tiles) {
+            // the next tile's operands start moving towards L2 now: one 128-byte line per thread and tensor slice
+            const long long nrow0 = (tile + gridDim.x) * kTileRows;
+            const long long nlines = min(static_cast<long long>(kTileRows), live - nrow0) * (kC * 4 / 128);   // row-major tensors
+            const int line = tid & 255;
+            const bool upper = tid >= 256;
+            if (!upper && line < nlines) prefetch_l2_line(grad_out + nrow0 * kC + line * 32);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                if (k < n_msgs) {
+                    if (upper && line < nlines) prefetch_l2_line(P.agg[k] + nrow0 * kC + line * 32);
+                    if ((tf || line < nlines)) prefetch_l2_line((upper ? P.saved_pre[k] : P.saved_m[k]) + nrow0 * kC + line * 32);
+                }
+            }
+        }
+        stamp();                                               // phase A done
         // ---------------- per message: two MMA rounds ----------------
         float dx[kCW];                                                        // row map
 #pragma unroll
@@ -334,15 +411,21 @@ __global__ void __launch_bounds__(kThreads, 1) combine_bwd_fused_kernel(topo_com
                 store_split8(p_img, kPart, ra + 64 * j, c, pre[j]);
                 if (k > 0) store_split8(q_img, kPart, ra + 64 * j, c, mq[j]);
             }
+            stamp();                                           // GELU' + images staged (before barrier)
             fence_async_shared();
             tc_fence_before_sync();
             __syncthreads();
-            if (warp == 0) {
+            stamp();                                           // barrier 1 passed
+            if (warp < 3) {
+                // three issuing threads share the 72 MMAs of the round (issue rate, not the tensor pipe, bounds a round)
                 if (lane == 0) {
                     tc_fence_after_sync();
-                    gemm_bf16x3_unrolled<kC / 16>(tm_t, k_major(p_s, kTileRows), mn_major(w1_s, kC, kWPart), idesc_bf16(128, 64, 0, 1), 0);
-                    gemm_bf16x3_unrolled<kTileRows / 16>(tm_dw1, mn_major(p_s, kTileRows, kPart), mn_major(q_s, kTileRows, kPart),
-                                                         idesc_bf16(64, 64, 1, 1), (tiles_done | static_cast<uint32_t>(k)) != 0u);
+                    if (warp == 0)
+                        gemm_bf16x3_unrolled<kC / 16>(tm_t, k_major(p_s, kTileRows), mn_major(w1_s, kC, kWPart), idesc_bf16(128, 64, 0, 1), 0);
+                    else if (warp == 1)
+                        gemm_bf16x3_unrolled<4, 0>(tm_dw1, mn_major(p_s, kTileRows, kPart), mn_major(q_s, kTileRows, kPart), idesc_bf16(64, 64, 1, 1), 1);
+                    else
+                        gemm_bf16x3_unrolled<4, 4>(tm_dw1, mn_major(p_s, kTileRows, kPart), mn_major(q_s, kTileRows, kPart), idesc_bf16(64, 64, 1, 1), 1);
                     mma_commit(bar);
                 }
                 __syncwarp();      // the other lanes park here instead of polling against the issuing lane
@@ -358,9 +441,11 @@ __global__ void __launch_bounds__(kThreads, 1) combine_bwd_fused_kernel(topo_com
                 t[4 * i] = v.x; t[4 * i + 1] = v.y; t[4 * i + 2] = v.z; t[4 * i + 3] = v.w;
             }
             const float ak = att_s[k * kTileRows + r];
+            stamp();                                           // round 1 issued, agg loads issued
             mbar_wait_backoff(bar, parity);
             parity ^= 1;
             tc_fence_after_sync();
+            stamp();                                           // round 1 complete
             {
                 float tt[kCW];
                 tmem_ld16(tm_t + lane_addr + col0, tt);
@@ -377,15 +462,19 @@ __global__ void __launch_bounds__(kThreads, 1) combine_bwd_fused_kernel(topo_com
             }
 #pragma unroll
             for (int j = 0; j < 2; ++j) store_split8(q_img, kPart, ra + 64 * j, c, ag[j]);
+            stamp();                                           // dm + agg images staged
             fence_async_shared();
             tc_fence_before_sync();
             __syncthreads();
-            if (warp == 0) {
+            if (warp < 3) {
                 if (lane == 0) {
                     tc_fence_after_sync();
-                    gemm_bf16x3_unrolled<kC / 16>(tm_ga, k_major(p_s, kTileRows), k_major(wk_s + k * kWImg, kC), idesc_bf16(128, 64, 0, 0), 0);
-                    gemm_bf16x3_unrolled<kTileRows / 16>(tm_dwp + k * 64, mn_major(q_s, kTileRows, kPart), mn_major(p_s, kTileRows, kPart),
-                                                         idesc_bf16(64, 64, 1, 1), tiles_done != 0u);
+                    if (warp == 0)
+                        gemm_bf16x3_unrolled<kC / 16>(tm_ga, k_major(p_s, kTileRows), k_major(wk_s + k * kWImg, kC), idesc_bf16(128, 64, 0, 0), 0);
+                    else if (warp == 1)
+                        gemm_bf16x3_unrolled<4, 0>(tm_dwp + k * 64, mn_major(q_s, kTileRows, kPart), mn_major(p_s, kTileRows, kPart), idesc_bf16(64, 64, 1, 1), 1);
+                    else
+                        gemm_bf16x3_unrolled<4, 4>(tm_dwp + k * 64, mn_major(q_s, kTileRows, kPart), mn_major(p_s, kTileRows, kPart), idesc_bf16(64, 64, 1, 1), 1);
                     mma_commit(bar);
                 }
                 __syncwarp();
@@ -396,6 +485,7 @@ __global__ void __launch_bounds__(kThreads, 1) combine_bwd_fused_kernel(topo_com
             }
         }
         // round 2 of the last message
+        stamp();                                               // last round 2 issued
         mbar_wait_backoff(bar, parity);
         parity ^= 1;
         tc_fence_after_sync();
@@ -417,6 +507,7 @@ __global__ void __launch_bounds__(kThreads, 1) combine_bwd_fused_kernel(topo_com
         }
         tc_fence_before_sync();
         __syncthreads();          // dy / a_k in shared memory are rewritten by the next tile's phase A
+        stamp();                                               // tile done
     }
 
     // ---------------- parameter gradients of this CTA ----------------
@@ -486,6 +577,10 @@ __global__ void __launch_bounds__(kThreads, 1) combine_bwd_fused_kernel(topo_com
 
 using namespace topo;
 
+static unsigned long long* g_bwd_stamps = nullptr;
+// globaltimer stamps of CTA 0 / thread 0 (up to 62 x uint64, see the stamp() calls) for scripts/ablate_bwd.py
+extern "C" void topo_debug_bwd_stamps(unsigned long long* device_buffer) { g_bwd_stamps = device_buffer; }
+
 extern "C" int topo_sccn_combine_bwd_tc(const topo_combine_params* p, int64_t rows, const int32_t* n_rows_dev,
                                         const float* grad_out, const topo_combine_grads* g, topo_stream_t stream) {
     TOPO_REQUIRE(p && g && grad_out && rows >= 0, "bad argument");
@@ -502,9 +597,17 @@ extern "C" int topo_sccn_combine_bwd_tc(const topo_combine_params* p, int64_t ro
     TOPO_REQUIRE(!p->apply_ln || (p->ln_gamma && g->g_ln_gamma && g->g_ln_beta), "null LayerNorm parameter");
     if (rows == 0) return TOPO_OK;
     const size_t smem = BwdSmem::kTotal;
-    if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(combine_bwd_fused_kernel), smem)) return rc;
     const int tiles = static_cast<int>((rows + kTileRows - 1) / kTileRows);
-    combine_bwd_fused_kernel<<<std::min(tiles, sm_count()), kThreads, smem, as_stream(stream)>>>(*p, rows, n_rows_dev, grad_out, *g);
+    const int grid = std::min(tiles, p->max_ctas > 0 ? std::min(p->max_ctas, sm_count()) : sm_count());
+#define TOPO_LAUNCH_BWD(NM)                                                                                                  \
+    do {                                                                                                                     \
+        if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(combine_bwd_fused_kernel<NM>), smem)) return rc;      \
+        combine_bwd_fused_kernel<NM><<<grid, kThreads, smem, as_stream(stream)>>>(*p, rows, n_rows_dev, grad_out, *g, g_bwd_stamps); \
+    } while (0)
+    if (p->n_msgs == 1) TOPO_LAUNCH_BWD(1);
+    else if (p->n_msgs == 2) TOPO_LAUNCH_BWD(2);
+    else TOPO_LAUNCH_BWD(3);
+#undef TOPO_LAUNCH_BWD
     TOPO_LAUNCH_CHECK();
     return TOPO_OK;
 }

@@ -610,7 +610,7 @@ extern "C" int topo_sccn_combine_fwd_tc(const topo_combine_params* p, int64_t ro
     const size_t smem = FwdSmem::kTotal + 1024;
     if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(combine_fwd_tc_kernel<4>), smem)) return rc;
     const int tiles = static_cast<int>((rows + kTileRows - 1) / kTileRows);
-    combine_fwd_tc_kernel<4><<<std::min(tiles, sm_count()), 512, smem, as_stream(stream)>>>(*p, rows, n_rows_dev, out);
+    combine_fwd_tc_kernel<4><<<std::min(tiles, p->max_ctas > 0 ? std::min(p->max_ctas, sm_count()) : sm_count()), 512, smem, as_stream(stream)>>>(*p, rows, n_rows_dev, out);
     TOPO_LAUNCH_CHECK();
     return TOPO_OK;
 }

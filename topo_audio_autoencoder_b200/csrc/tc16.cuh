@@ -104,7 +104,9 @@ __device__ __forceinline__ void gemm_bf16x3(uint32_t tmem_d, const Operand& a, c
 // Same product with the pass / k-step structure known at compile time: the issuing thread executes one
 // 32-bit add per operand and the MMA itself (the descriptor's 14-bit start-address field advances by the byte
 // offset >> 4; shared-memory addresses stay below 256 KB, so the add never carries out of the field).
-template <int KSTEPS>
+// K0: first k-step (several threads may each issue a k-range of one product into the same, already initialised
+// accumulator: the sum is order independent up to fp32 rounding).
+template <int KSTEPS, int K0 = 0>
 __device__ __forceinline__ void gemm_bf16x3_unrolled(uint32_t tmem_d, const Operand& a, const Operand& b, uint32_t idesc,
                                                      uint32_t accumulate_into) {
     const uint64_t a0 = smem_desc_sw128(a.base, a.lbo, a.sbo), b0 = smem_desc_sw128(b.base, b.lbo, b.sbo);
@@ -114,11 +116,16 @@ __device__ __forceinline__ void gemm_bf16x3_unrolled(uint32_t tmem_d, const Oper
         const uint32_t pa = pass == 0 ? 2u : ((pass == 2 || pass == 3) ? 1u : 0u);
         const uint32_t pb = pass == 1 ? 2u : ((pass == 2 || pass == 4) ? 1u : 0u);
 #pragma unroll
-        for (int k = 0; k < KSTEPS; ++k) {
+        for (int k = K0; k < K0 + KSTEPS; ++k) {
             mma_bf16(tmem_d, a0 + ((pa * a.part_stride + k * a.kstep) >> 4), b0 + ((pb * b.part_stride + k * b.kstep) >> 4), idesc, acc);
             acc = 1;
         }
     }
+}
+
+// hint: bring `bytes` (multiple of 16) starting at `p` into L2 ahead of the loads that will want them
+__device__ __forceinline__ void prefetch_l2(const void* p, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 
 }  // namespace tc16

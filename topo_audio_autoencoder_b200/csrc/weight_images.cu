@@ -66,10 +66,47 @@ __global__ void __launch_bounds__(512) prepare_images_kernel(const __grid_consta
     store_split8(dst + kWImg, kWPart, i, c, acc);
 }
 
+struct WgradJobs {
+    topo_wgrad_job j[kMaxJobs];
+};
+
+__global__ void __launch_bounds__(256) finish_weight_grads_kernel(const __grid_constant__ WgradJobs jobs, int n) {
+    __shared__ float part[8];
+    const topo_wgrad_job job = jobs.j[blockIdx.x];
+    const float s = __ldg(job.scale);
+    float acc = 0.f;
+    for (int i = threadIdx.x; i < n; i += 256) {
+        const float p = job.wprod[i];
+        job.g_w[i] = s * p;
+        acc = fmaf(p, __ldg(job.w + i), acc);
+    }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int w = 0; w < 8; ++w) t += part[w];
+        job.g_scale[0] = t;
+    }
+}
+
 }  // namespace
 }  // namespace topo
 
 using namespace topo;
+
+extern "C" int topo_sccn_finish_weight_grads(const topo_wgrad_job* jobs, int n_jobs, int channels, topo_stream_t stream) {
+    TOPO_REQUIRE(jobs && n_jobs >= 0 && n_jobs <= kMaxJobs && channels > 0, "1..16 jobs per call");
+    if (n_jobs == 0) return TOPO_OK;
+    WgradJobs packed{};
+    for (int q = 0; q < n_jobs; ++q) {
+        TOPO_REQUIRE(jobs[q].wprod && jobs[q].w && jobs[q].scale && jobs[q].g_w && jobs[q].g_scale, "null pointer in a weight-gradient job");
+        packed.j[q] = jobs[q];
+    }
+    finish_weight_grads_kernel<<<n_jobs, 256, 0, as_stream(stream)>>>(packed, channels * channels);
+    TOPO_LAUNCH_CHECK();
+    return TOPO_OK;
+}
 
 extern "C" int topo_sccn_prepare_images(const topo_image_job* jobs, int n_jobs, int channels, topo_stream_t stream) {
     TOPO_REQUIRE(jobs && n_jobs >= 0 && n_jobs <= kMaxJobs, "1..16 jobs per call");

@@ -25,7 +25,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from ._lib import (lib, check, ptr, ptr_array, stream, ComplexView, CombineParams, CombineGrads, ImageJob,
+from ._lib import (lib, check, ptr, ptr_array, stream, ComplexView, CombineParams, CombineGrads, ImageJob, WgradJob,
                    WEIGHT_IMAGE_BYTES)
 from .rectifier import _Tables
 
@@ -102,6 +102,8 @@ FORWARD_TC_GENERATION = 2
 # build the weights' operand images once per layer and step (one small launch) instead of inside every
 # tensor-core kernel launch
 SHARED_WEIGHT_IMAGES = True
+# launch the four ranks of a layer side by side (four streams, SMs divided by work) instead of one after another
+CONCURRENT_RANKS = True
 
 
 class _CombineFn(torch.autograd.Function):
@@ -182,8 +184,195 @@ class _CombineFn(torch.autograd.Function):
                 g_g if apply_ln else None, g_b if apply_ln else None, *g_aggs, *g_ws, *g_ss)
 
 
+# ---------------------------------------------------------------------------------------------------
+# one layer, all ranks: four tensor-core launches side by side
+# ---------------------------------------------------------------------------------------------------
+_SIDE_STREAMS: Dict[int, List[torch.cuda.Stream]] = {}
+
+
+def _side_streams(device: torch.device) -> List[torch.cuda.Stream]:
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    if idx not in _SIDE_STREAMS:
+        _SIDE_STREAMS[idx] = [torch.cuda.Stream(device=idx) for _ in range(3)]
+    return _SIDE_STREAMS[idx]
+
+
+def _sm_shares(costs: Sequence[float], n_sm: int) -> List[int]:
+    """Split the SMs between concurrent launches in proportion to their work (at least one each)."""
+    total = float(sum(costs)) or 1.0
+    live = [i for i, c in enumerate(costs) if c > 0]
+    shares = [0] * len(costs)
+    for i in live:
+        shares[i] = max(1, int(n_sm * costs[i] / total))
+    while sum(shares) > n_sm:                       # rounding up the small ones may overshoot
+        shares[max(live, key=lambda i: shares[i])] -= 1
+    if live:
+        shares[max(live, key=lambda i: costs[i])] += n_sm - sum(shares)
+    return shares
+
+
+class _Forked:
+    """Run rank launches concurrently: the largest on the current stream, the others on side streams that fork
+    from it and join back.  Torch's current stream never changes, so every allocation belongs to it."""
+
+    def __init__(self, device, order):
+        self.main = torch.cuda.current_stream(device)
+        self.side = _side_streams(device)
+        self.order = order                      # ranks, heaviest first
+        self.used = []
+        fork = torch.cuda.Event()
+        fork.record(self.main)
+        self.fork = fork
+
+    def stream_for(self, position: int) -> int:
+        if position == 0:
+            return self.main.cuda_stream
+        s = self.side[position - 1]
+        s.wait_event(self.fork)
+        self.used.append(s)
+        return s.cuda_stream
+
+    def join(self):
+        for s in self.used:
+            ev = torch.cuda.Event()
+            ev.record(s)
+            self.main.wait_event(ev)
+
+
+class _LayerCombineFn(torch.autograd.Function):
+    """The message combine of ALL ranks of one layer (tensor-core path, C = 64): what _CombineFn does per rank,
+    launched as four concurrent kernels with the SMs divided by work, one set of weight images, one zero fill
+    for every accumulated gradient and one launch for the conv-weight chain tail."""
+
+    @staticmethod
+    def forward(ctx, cfg, *flat):
+        ranks = cfg["ranks"]                    # per rank: dict(n_msgs, apply_ln, ln_eps, n_rows_dev, zero_dead_rows, has_x, images)
+        per, pos = [], 0
+        for rc in ranks:
+            n = rc["n_msgs"]
+            x = flat[pos] if rc["has_x"] else None
+            tens = [t.contiguous() for t in flat[pos + 1:pos + 7]]
+            aggs = [t.contiguous() for t in flat[pos + 7:pos + 7 + n]]
+            ws = [t.contiguous() for t in flat[pos + 7 + n:pos + 7 + 2 * n]]
+            scales = [t.contiguous() for t in flat[pos + 7 + 2 * n:pos + 7 + 3 * n]]
+            per.append(dict(x=x.contiguous() if x is not None else None, tens=tens, aggs=aggs, ws=ws, scales=scales, first=pos))
+            pos += 7 + 3 * n
+        dev = per[0]["aggs"][0].device
+        ch = per[0]["aggs"][0].shape[1]
+        need_grad = SAVE_ACTIVATIONS and any(ctx.needs_input_grad)
+        n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
+        costs = [float(pr["aggs"][0].shape[0]) * (rc["n_msgs"] + 1) for pr, rc in zip(per, ranks)]
+        shares = _sm_shares(costs, n_sm)
+        outs = []
+        for pr, rc in zip(per, ranks):
+            rows = pr["aggs"][0].shape[0]
+            pr["saved"] = None
+            if need_grad:
+                rows_alloc = -(-rows // 128) * 128
+                pr["saved"] = ([torch.empty(rows_alloc, ch, dtype=torch.float32, device=dev) for _ in range(rc["n_msgs"])],
+                               [torch.empty(rows_alloc, ch, dtype=torch.float32, device=dev) for _ in range(rc["n_msgs"])],
+                               torch.empty(3, rows, dtype=torch.float32, device=dev))
+            outs.append((torch.zeros if rc["zero_dead_rows"] else torch.empty)(rows, ch, dtype=torch.float32, device=dev))
+        order = sorted(range(len(ranks)), key=lambda i: -costs[i])
+        forked = _Forked(dev, order)
+        for position, i in enumerate(order):
+            pr, rc = per[i], ranks[i]
+            rows = pr["aggs"][0].shape[0]
+            if rows == 0:
+                continue
+            params = _make_params(ch, rc["n_msgs"], pr["aggs"], pr["ws"], pr["scales"], pr["x"], pr["tens"], rc["ln_eps"],
+                                  rc["apply_ln"], pr["saved"], need_grad, rc["images"], shares[i])
+            fwd = lib.topo_sccn_combine_fwd_tc2 if need_grad else lib.topo_sccn_combine_fwd_tc
+            check(fwd(C.byref(params), rows, ptr(rc["n_rows_dev"], torch.int32), ptr(outs[i]), forked.stream_for(position)))
+        forked.join()
+        ctx.per, ctx.ranks, ctx.shares, ctx.order = per, ranks, shares, order
+        ctx.n_flat = len(flat)
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *g_outs):
+        per, ranks, shares, order = ctx.per, ctx.ranks, ctx.shares, ctx.order
+        dev = per[0]["aggs"][0].device
+        ch = per[0]["aggs"][0].shape[1]
+        # one zero fill for everything the kernels accumulate into: per rank [wprod x n | w1 | b1 | w2 | b2 | gamma | beta]
+        sizes = [rc["n_msgs"] * ch * ch + ch * ch + 3 * ch + 1 + ch for rc in ranks]        # (+ ch: padding keeps 16-byte alignment)
+        sizes = [-(-sz // 4) * 4 for sz in sizes]
+        acc = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
+        grads_flat = [None] * ctx.n_flat
+        forked = _Forked(dev, order)
+        keep, jobs = [], []
+        off = 0
+        views = []
+        for i, (pr, rc) in enumerate(zip(per, ranks)):
+            n, base = rc["n_msgs"], off
+            v = {"wprod": [acc[base + k * ch * ch: base + (k + 1) * ch * ch].view(ch, ch) for k in range(n)]}
+            base += n * ch * ch
+            v["w1"] = acc[base:base + ch * ch].view(ch, ch); base += ch * ch
+            v["b1"] = acc[base:base + ch]; base += ch
+            v["w2"] = acc[base:base + ch]; base += ch
+            v["gamma"] = acc[base:base + ch]; base += ch
+            v["beta"] = acc[base:base + ch]; base += ch
+            v["b2"] = acc[base:base + 1]
+            views.append(v)
+            off += sizes[i]
+        for position, i in enumerate(order):
+            pr, rc, v = per[i], ranks[i], views[i]
+            rows, n = pr["aggs"][0].shape[0], rc["n_msgs"]
+            g_out = g_outs[i]
+            g_aggs = [torch.empty(rows, ch, dtype=torch.float32, device=dev) for _ in range(n)]
+            g_x = torch.empty(rows, ch, dtype=torch.float32, device=dev) if rc["has_x"] else None
+            pr["g_aggs"], pr["g_x"] = g_aggs, g_x
+            if rows == 0 or g_out is None:
+                for t in g_aggs:
+                    t.zero_()
+                if g_x is not None:
+                    g_x.zero_()
+                continue
+            g_out = g_out.contiguous()
+            keep.append(g_out)
+            params = _make_params(ch, n, pr["aggs"], pr["ws"], pr["scales"], pr["x"], pr["tens"], rc["ln_eps"], rc["apply_ln"],
+                                  pr["saved"], True, rc["images"], shares[i])
+            grads = CombineGrads()
+            for k in range(3):
+                grads.g_agg[k] = ptr(g_aggs[k]) if k < n else None
+                grads.g_wprod[k] = ptr(v["wprod"][k]) if k < n else None
+            grads.g_x = ptr(g_x)
+            grads.g_att_w1, grads.g_att_b1 = ptr(v["w1"]), ptr(v["b1"])
+            grads.g_att_w2, grads.g_att_b2 = ptr(v["w2"]), ptr(v["b2"])
+            grads.g_ln_gamma, grads.g_ln_beta = ptr(v["gamma"]), ptr(v["beta"])
+            check(lib.topo_sccn_combine_bwd_tc(C.byref(params), rows, ptr(rc["n_rows_dev"], torch.int32), ptr(g_out),
+                                               C.byref(grads), forked.stream_for(position)))
+        forked.join()
+        # conv-weight chain tail for every message of the layer in one launch: dW_k = s_k P_k, ds_k = <W_k, P_k>
+        n_total = sum(rc["n_msgs"] for rc in ranks)
+        g_w_all = torch.empty(n_total, ch, ch, dtype=torch.float32, device=dev)
+        g_s_all = torch.empty(n_total, dtype=torch.float32, device=dev)
+        arr = (WgradJob * n_total)()
+        q = 0
+        for i, (pr, rc) in enumerate(zip(per, ranks)):
+            for k in range(rc["n_msgs"]):
+                arr[q].wprod, arr[q].w, arr[q].scale = ptr(views[i]["wprod"][k]), ptr(pr["ws"][k]), ptr(pr["scales"][k])
+                arr[q].g_w, arr[q].g_scale = g_w_all[q].data_ptr(), g_s_all[q:q + 1].data_ptr()
+                q += 1
+        check(lib.topo_sccn_finish_weight_grads(arr, n_total, ch, stream()))
+        q = 0
+        for i, (pr, rc) in enumerate(zip(per, ranks)):
+            n, first, v = rc["n_msgs"], pr["first"], views[i]
+            if rc["has_x"]:
+                grads_flat[first] = pr["g_x"]
+            grads_flat[first + 1:first + 5] = [v["w1"], v["b1"], v["w2"], v["b2"]]
+            if rc["apply_ln"]:
+                grads_flat[first + 5], grads_flat[first + 6] = v["gamma"], v["beta"]
+            for k in range(n):
+                grads_flat[first + 7 + k] = pr["g_aggs"][k]
+                grads_flat[first + 7 + n + k] = g_w_all[q]
+                grads_flat[first + 7 + 2 * n + k] = g_s_all[q:q + 1].reshape(pr["scales"][k].shape)
+                q += 1
+        return (None, *grads_flat)
+
+
 def _make_params(ch, n_msgs, aggs, ws, scales, x, tensors, ln_eps, apply_ln, saved=None, tile_fragment=False,
-                 images: Optional[torch.Tensor] = None) -> CombineParams:
+                 images: Optional[torch.Tensor] = None, max_ctas: int = 0) -> CombineParams:
     p = CombineParams()
     p.channels, p.n_msgs = ch, n_msgs
     for k in range(3):
@@ -195,6 +384,7 @@ def _make_params(ch, n_msgs, aggs, ws, scales, x, tensors, ln_eps, apply_ln, sav
     p.saved_score = ptr(saved[2]) if (saved is not None and len(saved) > 2) else None
     p.saved_layout = 1 if tile_fragment else 0       # TOPO_SAVED_TILE_FRAGMENT / TOPO_SAVED_ROW_MAJOR
     p.weight_images = ptr(images, torch.uint8) if images is not None else None
+    p.max_ctas = int(max_ctas)
     p.x = ptr(x)
     p.att_w1, p.att_b1, p.att_w2, p.att_b2 = (ptr(t) for t in tensors[:4])
     p.ln_gamma, p.ln_beta = ptr(tensors[4]), ptr(tensors[5])
@@ -390,7 +580,19 @@ class GradientSCCNLayer(nn.Module):
             if r > 0:
                 msgs.append((up[r], self.convs_low_to_high[key].weight, sc["low_to_high"]))
             per_rank.append((key, msgs))
-        images = self._weight_images(per_rank, xs[0].device) if (COMBINE_IMPL == "tc" and self.channels == 64 and SHARED_WEIGHT_IMAGES) else [None] * 4
+        tc = COMBINE_IMPL == "tc" and self.channels == 64
+        images = self._weight_images(per_rank, xs[0].device) if (tc and SHARED_WEIGHT_IMAGES) else [None] * 4
+        if tc and CONCURRENT_RANKS and FORWARD_TC_GENERATION == 2 and all(cx.rows_max[r] for r in range(4)):
+            apply_ln = self.training and not self.is_final_layer
+            ranks, flat = [], []
+            for r, (key, msgs) in enumerate(per_rank):
+                att, ln = self.message_attention[key], self.layer_norms[key]
+                aggs, ws, scales = zip(*msgs)
+                ranks.append(dict(n_msgs=len(msgs), apply_ln=apply_ln, ln_eps=ln.eps, n_rows_dev=cx.live_rows(r),
+                                  zero_dead_rows=zero_dead_rows, has_x=self.residual, images=images[r]))
+                flat += [xs[r], att[0].weight, att[0].bias, att[2].weight.reshape(-1), att[2].bias, ln.weight, ln.bias,
+                         *aggs, *ws, *scales]
+            return list(_LayerCombineFn.apply(dict(ranks=ranks), *flat))
         out = []
         for r, (key, msgs) in enumerate(per_rank):
             out.append(self._combine(key, xs[r], msgs, cx.live_rows(r), zero_dead_rows, images[r]) if cx.rows_max[r] else xs[r])
