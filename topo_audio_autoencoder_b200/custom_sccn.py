@@ -104,6 +104,9 @@ FORWARD_TC_GENERATION = 2
 SHARED_WEIGHT_IMAGES = True
 # launch the four ranks of a layer side by side (four streams, SMs divided by work) instead of one after another
 CONCURRENT_RANKS = True
+# make the neighbourhood aggregation part of the same autograd node as the combine: its backward then works on the
+# node's own gradient buffers (no clones of the in-place updated ones, no zero fills, no autograd additions)
+FUSED_LAYER_NODE = True
 
 
 class _CombineFn(torch.autograd.Function):
@@ -247,16 +250,40 @@ class _LayerCombineFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, cfg, *flat):
         ranks = cfg["ranks"]                    # per rank: dict(n_msgs, apply_ln, ln_eps, n_rows_dev, zero_dead_rows, has_x, images)
-        per, pos = [], 0
+        cx = cfg.get("cx")                      # given: the neighbourhood aggregation is part of this node (flat[0] = probs, no aggregates in flat)
+        per, pos = [], (1 if cx is not None else 0)
+        n_agg = 0 if cx is not None else 1
         for rc in ranks:
             n = rc["n_msgs"]
-            x = flat[pos] if rc["has_x"] else None
+            xin = flat[pos].contiguous()
             tens = [t.contiguous() for t in flat[pos + 1:pos + 7]]
-            aggs = [t.contiguous() for t in flat[pos + 7:pos + 7 + n]]
-            ws = [t.contiguous() for t in flat[pos + 7 + n:pos + 7 + 2 * n]]
-            scales = [t.contiguous() for t in flat[pos + 7 + 2 * n:pos + 7 + 3 * n]]
-            per.append(dict(x=x.contiguous() if x is not None else None, tens=tens, aggs=aggs, ws=ws, scales=scales, first=pos))
-            pos += 7 + 3 * n
+            aggs = [t.contiguous() for t in flat[pos + 7:pos + 7 + n * n_agg]]
+            ws = [t.contiguous() for t in flat[pos + 7 + n * n_agg:pos + 7 + n * (n_agg + 1)]]
+            scales = [t.contiguous() for t in flat[pos + 7 + n * (n_agg + 1):pos + 7 + n * (n_agg + 2)]]
+            per.append(dict(x=xin if rc["has_x"] else None, xin=xin, tens=tens, aggs=aggs, ws=ws, scales=scales, first=pos))
+            pos += 7 + n * (n_agg + 2)
+        if cx is not None:
+            # down[r] = I_{r+1} X_{r+1}, up[r] = I_r^T X_{r-1}, same[r] = A_r X_r for the whole batch (csrc/aggregate.cu)
+            probs = flat[0].contiguous()
+            xs = [pr["xin"] for pr in per]
+            ch_, dev_ = xs[0].shape[1], probs.device
+            counts = cx.tables.counts
+
+            def new(r, source_rank=None):
+                empty_source = source_rank is not None and counts[source_rank] == 0
+                return (torch.zeros if empty_source else torch.empty)(cx.rows_max[r], ch_, dtype=torch.float32, device=dev_)
+
+            down = [new(0, 1), new(1, 2), new(2, 3), None]
+            up = [None, new(1), new(2), new(3)]
+            same = [new(r) for r in range(4)]
+            view = cx.view(probs)
+            check(lib.topo_sccn_aggregate_fwd(cx.tables.handle, C.byref(view), ch_, ptr_array(xs, 4), ptr_array(down, 4),
+                                              ptr_array(up, 4), ptr_array(same, 4), stream()))
+            for r, pr in enumerate(per):
+                pr["aggs"] = [same[r]] + ([down[r]] if r < 3 else []) + ([up[r]] if r > 0 else [])
+            ctx.agg = dict(cx=cx, probs=probs, xs=xs, down2=down[2], up2=up[2], up3=up[3])
+        else:
+            ctx.agg = None
         dev = per[0]["aggs"][0].device
         ch = per[0]["aggs"][0].shape[1]
         need_grad = SAVE_ACTIVATIONS and any(ctx.needs_input_grad)
@@ -355,18 +382,42 @@ class _LayerCombineFn(torch.autograd.Function):
                 arr[q].g_w, arr[q].g_scale = g_w_all[q].data_ptr(), g_s_all[q:q + 1].data_ptr()
                 q += 1
         check(lib.topo_sccn_finish_weight_grads(arr, n_total, ch, stream()))
+        agg = ctx.agg
+        if agg is not None:
+            # the aggregation backward runs on this node's own buffers: it updates g_down[2], g_up[2], g_up[3] in
+            # place and ACCUMULATES into the residual gradients the combine kernels just wrote (no clones, no zero
+            # fills, no autograd additions)
+            cx = agg["cx"]
+            g_same = [per[r]["g_aggs"][0] for r in range(4)]
+            g_down = [per[r]["g_aggs"][1] for r in range(3)] + [None]
+            g_up = [None] + [per[r]["g_aggs"][2 if r < 3 else 1] for r in range(1, 4)]
+            g_x = [pr["g_x"] if pr["g_x"] is not None else torch.zeros_like(pr["xin"]) for pr in per]
+            g_probs = torch.zeros_like(agg["probs"])
+            view = cx.view(agg["probs"])
+            check(lib.topo_sccn_aggregate_bwd(cx.tables.handle, C.byref(view), ch, ptr_array(agg["xs"], 4),
+                                              ptr_array([None, None, agg["down2"], None], 4),
+                                              ptr_array([None, None, agg["up2"], agg["up3"]], 4),
+                                              ptr_array(g_down, 4), ptr_array(g_up, 4), ptr_array(g_same, 4),
+                                              ptr_array(g_x, 4), ptr(g_probs), stream()))
+            grads_flat[0] = g_probs
+            for pr, gx in zip(per, g_x):
+                pr["g_x_total"] = gx
+        n_agg = 0 if agg is not None else 1
         q = 0
         for i, (pr, rc) in enumerate(zip(per, ranks)):
             n, first, v = rc["n_msgs"], pr["first"], views[i]
-            if rc["has_x"]:
+            if agg is not None:
+                grads_flat[first] = pr["g_x_total"]
+            elif rc["has_x"]:
                 grads_flat[first] = pr["g_x"]
             grads_flat[first + 1:first + 5] = [v["w1"], v["b1"], v["w2"], v["b2"]]
             if rc["apply_ln"]:
                 grads_flat[first + 5], grads_flat[first + 6] = v["gamma"], v["beta"]
             for k in range(n):
-                grads_flat[first + 7 + k] = pr["g_aggs"][k]
-                grads_flat[first + 7 + n + k] = g_w_all[q]
-                grads_flat[first + 7 + 2 * n + k] = g_s_all[q:q + 1].reshape(pr["scales"][k].shape)
+                if n_agg:
+                    grads_flat[first + 7 + k] = pr["g_aggs"][k]
+                grads_flat[first + 7 + n * n_agg + k] = g_w_all[q]
+                grads_flat[first + 7 + n * (n_agg + 1) + k] = g_s_all[q:q + 1].reshape(pr["scales"][k].shape)
                 q += 1
         return (None, *grads_flat)
 
@@ -568,9 +619,15 @@ class GradientSCCNLayer(nn.Module):
     def forward_complex(self, cx: BatchedComplex, xs: Sequence[torch.Tensor], zero_dead_rows: bool = True) -> List[torch.Tensor]:
         if self.max_rank != 3:
             raise ValueError("forward_complex is built for the reference's max_rank = 3 complexes")
-        d0, d1, d2, u1, u2, u3, s0, s1, s2, s3 = _AggregateFn.apply(cx, cx.probs, *xs)
-        same, down, up = (s0, s1, s2, s3), (d0, d1, d2, None), (None, u1, u2, u3)
         sc = self.message_scales
+        tc = COMBINE_IMPL == "tc" and self.channels == 64
+        layer_node = tc and CONCURRENT_RANKS and FORWARD_TC_GENERATION == 2 and all(cx.rows_max[r] for r in range(4))
+        fused_agg = layer_node and FUSED_LAYER_NODE
+        if fused_agg:
+            same = down = up = (None, None, None, None)        # formed inside the layer node
+        else:
+            d0, d1, d2, u1, u2, u3, s0, s1, s2, s3 = _AggregateFn.apply(cx, cx.probs, *xs)
+            same, down, up = (s0, s1, s2, s3), (d0, d1, d2, None), (None, u1, u2, u3)
         per_rank = []
         for r in range(4):
             key = f"rank_{r}"
@@ -580,19 +637,18 @@ class GradientSCCNLayer(nn.Module):
             if r > 0:
                 msgs.append((up[r], self.convs_low_to_high[key].weight, sc["low_to_high"]))
             per_rank.append((key, msgs))
-        tc = COMBINE_IMPL == "tc" and self.channels == 64
         images = self._weight_images(per_rank, xs[0].device) if (tc and SHARED_WEIGHT_IMAGES) else [None] * 4
-        if tc and CONCURRENT_RANKS and FORWARD_TC_GENERATION == 2 and all(cx.rows_max[r] for r in range(4)):
+        if layer_node:
             apply_ln = self.training and not self.is_final_layer
-            ranks, flat = [], []
+            ranks, flat = [], ([cx.probs] if fused_agg else [])
             for r, (key, msgs) in enumerate(per_rank):
                 att, ln = self.message_attention[key], self.layer_norms[key]
                 aggs, ws, scales = zip(*msgs)
                 ranks.append(dict(n_msgs=len(msgs), apply_ln=apply_ln, ln_eps=ln.eps, n_rows_dev=cx.live_rows(r),
                                   zero_dead_rows=zero_dead_rows, has_x=self.residual, images=images[r]))
                 flat += [xs[r], att[0].weight, att[0].bias, att[2].weight.reshape(-1), att[2].bias, ln.weight, ln.bias,
-                         *aggs, *ws, *scales]
-            return list(_LayerCombineFn.apply(dict(ranks=ranks), *flat))
+                         *([] if fused_agg else aggs), *ws, *scales]
+            return list(_LayerCombineFn.apply(dict(ranks=ranks, cx=cx if fused_agg else None), *flat))
         out = []
         for r, (key, msgs) in enumerate(per_rank):
             out.append(self._combine(key, xs[r], msgs, cx.live_rows(r), zero_dead_rows, images[r]) if cx.rows_max[r] else xs[r])
