@@ -274,7 +274,7 @@ typedef struct {
 /* bf16x3 operand images of the weights (csrc/weight_images.cu), built once per layer and step and shared by the
  * forward and backward tensor-core kernels of all ranks.  A job with `w` writes the image of W_k [in][out]
  * (24,576 bytes) followed by the image of V_k = s_k W_k W1^T (24,576 bytes) to dst; a job with w == NULL writes
- * the image of W1 [out][in] (24,576 bytes).  At most 16 jobs per call, one CTA each. */
+ * the image of W1 [out][in] (24,576 bytes).  At most 96 jobs per call (all layers of a 6-layer SCCN), one CTA each. */
 typedef struct {
     const float* w;
     const float* scale;
@@ -284,7 +284,7 @@ typedef struct {
 #define TOPO_WEIGHT_IMAGE_BYTES 24576
 int topo_sccn_prepare_images(const topo_image_job* jobs, int n_jobs, int channels, topo_stream_t stream);
 
-/* The tail of the conv-weight chain for up to 16 messages in one launch (one CTA each, deterministic):
+/* The tail of the conv-weight chain for up to 96 messages in one launch (one CTA each, deterministic):
  *   g_w = scale * wprod   ([C, C]),   g_scale[0] = <w, wprod>      with wprod = g_wprod of topo_combine_grads. */
 typedef struct {
     const float* wprod;

@@ -1,4 +1,5 @@
 """GPU: in-kernel timeline (globaltimer) of the fused backward at the rank-3 size."""
+# needs a debug build of the library:  TOPO_DEBUG_KERNELS=1 python topo_audio_autoencoder_b200/csrc/build.py --force
 import ctypes as C
 import sys
 import torch

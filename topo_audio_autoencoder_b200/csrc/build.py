@@ -19,6 +19,8 @@ SOURCES = ["tables.cu", "gate.cu", "rectifier.cu", "operators.cu", "aggregate.cu
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
          "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
          "-I", os.path.join(ROOT, "include"), "-I", HERE]
+if os.environ.get("TOPO_DEBUG_KERNELS", "0") not in ("", "0"):
+    FLAGS.append("-DTOPO_DEBUG_KERNELS=1")      # ablation knobs + globaltimer stamps in the tensor-core kernels (scripts/ablate_*.py)
 
 
 def _digest(sources):

@@ -24,6 +24,10 @@
 #include "layout.cuh"
 #include "tc16.cuh"
 
+#ifndef TOPO_DEBUG_KERNELS
+#define TOPO_DEBUG_KERNELS 0
+#endif
+
 namespace topo {
 namespace {
 
@@ -137,14 +141,18 @@ __global__ void __launch_bounds__(kThreads, 1) combine_bwd_fused_kernel(topo_com
                                                                         const float* __restrict__ grad_out,
                                                                         topo_combine_grads G,
                                                                         unsigned long long* __restrict__ stamps) {
+    // in-kernel timeline for scripts/ablate_bwd.py: compiled in only with -DTOPO_DEBUG_KERNELS=1 (build.py reads the
+    // environment variable of that name); the shipped build has no trace of it
     int stamp_no = 0;
     auto stamp = [&]() {
+#if TOPO_DEBUG_KERNELS
         if (stamps != nullptr && blockIdx.x == 0 && threadIdx.x == 0 && stamp_no < 62) {
             unsigned long long t;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
             stamps[stamp_no] = t;
         }
         ++stamp_no;
+#endif
     };
     stamp();                                                   // 0: kernel start
     extern __shared__ __align__(1024) uint8_t smem_raw[];

@@ -22,6 +22,10 @@
 #include "layout.cuh"
 #include "tc16.cuh"
 
+#ifndef TOPO_DEBUG_KERNELS
+#define TOPO_DEBUG_KERNELS 0
+#endif
+
 namespace topo {
 namespace {
 
@@ -82,12 +86,21 @@ __global__ void __launch_bounds__(kThreads, 1) combine_fwd16_kernel(topo_combine
     uint64_t* bars = reinterpret_cast<uint64_t*>(base + FwdSmem16::kBar);       // one per operand slot
     uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(base + FwdSmem16::kBar + 16);
 
+    // differential-timing knobs and the in-kernel timeline of scripts/ablate_fwd16.py exist only in builds with
+    // -DTOPO_DEBUG_KERNELS=1 (build.py reads the environment variable of that name)
+#if !TOPO_DEBUG_KERNELS
+    dbg = 0;
+#endif
     auto stamp = [&](int slot) {
+#if TOPO_DEBUG_KERNELS
         if (stamps != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
             unsigned long long t;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
             stamps[slot] = t;
         }
+#else
+        (void)slot;
+#endif
     };
     stamp(0);
     const long long live = n_rows_dev ? min(static_cast<long long>(*n_rows_dev), rows) : rows;

@@ -17,7 +17,7 @@ using namespace tc16;
 constexpr int kC = 64;
 constexpr uint32_t kWPart = kC * 128;
 constexpr uint32_t kWImg = 3 * kWPart;
-constexpr int kMaxJobs = 16;
+constexpr int kMaxJobs = 96;          // 96 x 32 bytes of kernel parameters: every layer of a 6-layer SCCN in one launch
 
 struct ImageJobs {
     topo_image_job j[kMaxJobs];
@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(256) finish_weight_grads_kernel(const __grid_c
 using namespace topo;
 
 extern "C" int topo_sccn_finish_weight_grads(const topo_wgrad_job* jobs, int n_jobs, int channels, topo_stream_t stream) {
-    TOPO_REQUIRE(jobs && n_jobs >= 0 && n_jobs <= kMaxJobs && channels > 0, "1..16 jobs per call");
+    TOPO_REQUIRE(jobs && n_jobs >= 0 && n_jobs <= kMaxJobs && channels > 0, "at most 96 jobs per call");
     if (n_jobs == 0) return TOPO_OK;
     WgradJobs packed{};
     for (int q = 0; q < n_jobs; ++q) {
@@ -109,7 +109,7 @@ extern "C" int topo_sccn_finish_weight_grads(const topo_wgrad_job* jobs, int n_j
 }
 
 extern "C" int topo_sccn_prepare_images(const topo_image_job* jobs, int n_jobs, int channels, topo_stream_t stream) {
-    TOPO_REQUIRE(jobs && n_jobs >= 0 && n_jobs <= kMaxJobs, "1..16 jobs per call");
+    TOPO_REQUIRE(jobs && n_jobs >= 0 && n_jobs <= kMaxJobs, "at most 96 jobs per call");
     if (channels != kC) {
         set_error("weight images exist for channels == 64 (the tensor-core kernels)");
         return TOPO_ERR_UNSUPPORTED;

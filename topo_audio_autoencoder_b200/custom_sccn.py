@@ -616,7 +616,8 @@ class GradientSCCNLayer(nn.Module):
         return out
 
     # -- batch of complexes, matrix-free --------------------------------------------------------
-    def forward_complex(self, cx: BatchedComplex, xs: Sequence[torch.Tensor], zero_dead_rows: bool = True) -> List[torch.Tensor]:
+    def forward_complex(self, cx: BatchedComplex, xs: Sequence[torch.Tensor], zero_dead_rows: bool = True,
+                        images: Optional[List[torch.Tensor]] = None) -> List[torch.Tensor]:
         if self.max_rank != 3:
             raise ValueError("forward_complex is built for the reference's max_rank = 3 complexes")
         sc = self.message_scales
@@ -637,7 +638,8 @@ class GradientSCCNLayer(nn.Module):
             if r > 0:
                 msgs.append((up[r], self.convs_low_to_high[key].weight, sc["low_to_high"]))
             per_rank.append((key, msgs))
-        images = self._weight_images(per_rank, xs[0].device) if (tc and SHARED_WEIGHT_IMAGES) else [None] * 4
+        if images is None:
+            images = self._weight_images(xs[0].device) if (tc and SHARED_WEIGHT_IMAGES) else [None] * 4
         if layer_node:
             apply_ln = self.training and not self.is_final_layer
             ranks, flat = [], ([cx.probs] if fused_agg else [])
@@ -654,27 +656,48 @@ class GradientSCCNLayer(nn.Module):
             out.append(self._combine(key, xs[r], msgs, cx.live_rows(r), zero_dead_rows, images[r]) if cx.rows_max[r] else xs[r])
         return out
 
-    def _weight_images(self, per_rank, device) -> List[torch.Tensor]:
-        """bf16x3 operand images of this layer's weights for all ranks, built by ONE launch (csrc/weight_images.cu)
-        and shared by the forward and backward tensor-core kernels: per rank [W1 | k: W_k, V_k = s_k W_k W1^T]."""
-        sizes = [WEIGHT_IMAGE_BYTES * (1 + 2 * len(msgs)) for _, msgs in per_rank]
-        buf = torch.empty(sum(sizes), dtype=torch.uint8, device=device)
-        views, jobs, off = [], [], 0
-        for (key, msgs), size in zip(per_rank, sizes):
-            views.append(buf[off:off + size])
-            w1 = self.message_attention[key][0].weight.detach().contiguous()
+    def _image_jobs(self):
+        """[(rank key, [(W_k, s_k), ...])] in the message order of forward_complex: same, from above, from below."""
+        sc = self.message_scales
+        out = []
+        for r in range(4):
+            key = f"rank_{r}"
+            msgs = [(self.convs_same_rank[key].weight, sc["same_rank"])]
+            if r < 3:
+                msgs.append((self.convs_high_to_low[key].weight, sc["high_to_low"]))
+            if r > 0:
+                msgs.append((self.convs_low_to_high[key].weight, sc["low_to_high"]))
+            out.append((key, msgs))
+        return out
+
+    def _weight_images(self, device) -> List[torch.Tensor]:
+        return prepare_weight_images([self], device)[0]
+
+
+def prepare_weight_images(layers, device) -> List[List[torch.Tensor]]:
+    """bf16x3 operand images of the weights of `layers` for all ranks, built by ONE launch (csrc/weight_images.cu)
+    and shared by the forward and backward tensor-core kernels: per layer and rank [W1 | k: W_k, V_k = s_k W_k W1^T]."""
+    plan = [layer._image_jobs() for layer in layers]
+    sizes = [[WEIGHT_IMAGE_BYTES * (1 + 2 * len(msgs)) for _, msgs in per_rank] for per_rank in plan]
+    buf = torch.empty(sum(sum(sz) for sz in sizes), dtype=torch.uint8, device=device)
+    views, jobs, off = [], [], 0
+    for layer, per_rank, sz in zip(layers, plan, sizes):
+        views.append([])
+        for (key, msgs), size in zip(per_rank, sz):
+            views[-1].append(buf[off:off + size])
+            w1 = layer.message_attention[key][0].weight.detach().contiguous()
             base = buf.data_ptr() + off
             jobs.append((None, None, w1, base))
-            for k, (_, w, s) in enumerate(msgs):
+            for k, (w, s) in enumerate(msgs):
                 jobs.append((w.detach().contiguous(), s.detach().contiguous(), w1, base + WEIGHT_IMAGE_BYTES * (1 + 2 * k)))
             off += size
-        arr = (ImageJob * len(jobs))()
-        keep = []
-        for q, (w, s, w1, dst) in enumerate(jobs):
+    for first in range(0, len(jobs), 96):
+        chunk = jobs[first:first + 96]
+        arr = (ImageJob * len(chunk))()
+        for q, (w, s, w1, dst) in enumerate(chunk):
             arr[q].w, arr[q].scale, arr[q].att_w1, arr[q].dst = ptr(w), ptr(s), ptr(w1), dst
-            keep.append((w, s, w1))
-        check(lib.topo_sccn_prepare_images(arr, len(jobs), self.channels, stream()))
-        return views
+        check(lib.topo_sccn_prepare_images(arr, len(chunk), layers[0].channels, stream()))
+    return views
 
 
 class GradientSCCN(nn.Module):
@@ -697,6 +720,9 @@ class GradientSCCN(nn.Module):
         return features
 
     def forward_complex(self, cx: BatchedComplex, xs: Sequence[torch.Tensor]) -> List[torch.Tensor]:
+        images = [None] * len(self.layers)
+        if COMBINE_IMPL == "tc" and self.channels == 64 and SHARED_WEIGHT_IMAGES and self.max_rank == 3:
+            images = prepare_weight_images(list(self.layers), xs[0].device)      # every layer's weights in one launch
         for i, layer in enumerate(self.layers):
-            xs = layer.forward_complex(cx, xs, zero_dead_rows=(i == len(self.layers) - 1))
+            xs = layer.forward_complex(cx, xs, zero_dead_rows=(i == len(self.layers) - 1), images=images[i])
         return list(xs)
