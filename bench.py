@@ -134,6 +134,8 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1 to its workers; the reference arm is one process and may use every host core
+    torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
     ref = CpuReference(args)
     per = args.ref_clips_per_step
     for _ in range(args.warmup):
@@ -396,6 +398,7 @@ def run_ours(args):
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
+        torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
         ref = CpuReference(args)
         ref.time_clips(1)
         t = ref.time_clips(args.cpu_samples)

@@ -83,3 +83,36 @@ def test_gradient_allreduce_world_size_2_gloo(tmp_path):
     model(data).mean().backward()
     want = torch.cat([p.grad.reshape(-1) for p in model.parameters()])
     assert torch.allclose(got, want, rtol=1e-6, atol=1e-7)
+
+
+def test_sm_partition_between_concurrent_rank_launches():
+    """custom_sccn._sm_shares: every live launch gets at least one SM, the shares add up to the SM count, and
+    they follow the work (the four ranks of a layer run side by side on these partitions)."""
+    from topo_audio_autoencoder_b200.custom_sccn import _sm_shares
+    full = [1280 * 3, 12160 * 4, 72960 * 4, 310080 * 3]            # rows x (messages + 1) of the full 20-vertex complex, 64 clips
+    s = _sm_shares(full, 148)
+    assert sum(s) == 148 and min(s) >= 1
+    assert s[3] > s[2] > s[1] >= s[0]
+    assert abs(s[3] - 148 * full[3] / sum(full)) <= 4
+    assert _sm_shares([0, 5, 0, 5], 148) == [0, 74, 0, 74]
+    assert sum(_sm_shares([1, 1, 1, 10 ** 9], 8)) == 8 and min(_sm_shares([1, 1, 1, 10 ** 9], 8)) >= 1
+    assert _sm_shares([0, 0, 0, 0], 148) == [0, 0, 0, 0]
+
+
+def test_tile_fragment_layout_is_a_permutation_of_each_tile():
+    """layout.cuh: float4 index = tile * 2048 + (q * 4 + j) * 128 + r; the chunk-map view addresses the same
+    elements (the test mirrors the two device functions)."""
+    import numpy as np
+    rows = 3 * 128
+    seen = np.zeros(rows * 16, dtype=np.int64)
+    for row in range(rows):
+        row0, r = (row // 128) * 128, row % 128
+        for q in range(4):
+            base = (row0 >> 7) * 2048 + q * 512 + r                # tf_index(row0, q, r)
+            for j in range(4):
+                seen[base + j * 128] += 1
+        for c in range(8):                                         # tf_index_chunk(row0, r, c) and + 128
+            base = (row0 >> 7) * 2048 + ((c >> 1) * 4 + (c & 1) * 2) * 128 + r
+            q, j0 = c // 2, (c % 2) * 2
+            assert base == (row0 >> 7) * 2048 + (q * 4 + j0) * 128 + r
+    assert (seen == 1).all()

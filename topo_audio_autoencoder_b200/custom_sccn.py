@@ -18,6 +18,7 @@ weight [in, out], Xavier-uniform gain 1.414.  The kernels evaluate it as
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -103,7 +104,7 @@ FORWARD_TC_GENERATION = 2
 # tensor-core kernel launch
 SHARED_WEIGHT_IMAGES = True
 # launch the four ranks of a layer side by side (four streams, SMs divided by work) instead of one after another
-CONCURRENT_RANKS = True
+CONCURRENT_RANKS = os.environ.get("TOPO_CONCURRENT_RANKS", "1") not in ("0", "")      # 0: one rank after another, full grid each (profiling)
 # make the neighbourhood aggregation part of the same autograd node as the combine: its backward then works on the
 # node's own gradient buffers (no clones of the in-place updated ones, no zero fills, no autograd additions)
 FUSED_LAYER_NODE = True
