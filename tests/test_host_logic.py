@@ -86,16 +86,20 @@ def test_gradient_allreduce_world_size_2_gloo(tmp_path):
 
 
 def test_sm_partition_between_concurrent_rank_launches():
-    """custom_sccn._sm_shares: every live launch gets at least one SM, the shares add up to the SM count, and
-    they follow the work (the four ranks of a layer run side by side on these partitions)."""
+    """custom_sccn._sm_shares: every live launch gets at least one SM, never more than it has tiles, the shares
+    use the whole GPU when there is enough work, and the launches finish together (the four ranks of a layer run
+    side by side on these partitions)."""
     from topo_audio_autoencoder_b200.custom_sccn import _sm_shares
-    full = [1280 * 3, 12160 * 4, 72960 * 4, 310080 * 3]            # rows x (messages + 1) of the full 20-vertex complex, 64 clips
-    s = _sm_shares(full, 148)
+    tiles = [10, 95, 570, 2423]                                   # 128-row tiles of the full 20-vertex complex, 64 clips
+    costs = [t * (n + 1.2) for t, n in zip(tiles, (2, 3, 3, 2))]
+    s = _sm_shares(costs, 148, tiles)
     assert sum(s) == 148 and min(s) >= 1
     assert s[3] > s[2] > s[1] >= s[0]
-    assert abs(s[3] - 148 * full[3] / sum(full)) <= 4
-    assert _sm_shares([0, 5, 0, 5], 148) == [0, 74, 0, 74]
-    assert sum(_sm_shares([1, 1, 1, 10 ** 9], 8)) == 8 and min(_sm_shares([1, 1, 1, 10 ** 9], 8)) >= 1
+    finish = [-(-t // k) * c / t for t, k, c in zip(tiles, s, costs)]
+    assert max(finish[1:]) / min(finish[1:]) < 1.15, finish       # the three big launches end within 15 % of each other
+    assert _sm_shares([0, 5, 0, 5], 148, [0, 5, 0, 5]) == [0, 5, 0, 5]      # one CTA per tile is the most a launch can use
+    small = _sm_shares([1, 1, 1, 10 ** 9], 8, [1, 1, 1, 1000])
+    assert sum(small) == 8 and small[:3] == [1, 1, 1]
     assert _sm_shares([0, 0, 0, 0], 148) == [0, 0, 0, 0]
 
 

@@ -201,17 +201,33 @@ def _side_streams(device: torch.device) -> List[torch.cuda.Stream]:
     return _SIDE_STREAMS[idx]
 
 
-def _sm_shares(costs: Sequence[float], n_sm: int) -> List[int]:
-    """Split the SMs between concurrent launches in proportion to their work (at least one each)."""
-    total = float(sum(costs)) or 1.0
+def _sm_shares(costs: Sequence[float], n_sm: int, units: Optional[Sequence[int]] = None) -> List[int]:
+    """Split the SMs between concurrent persistent launches so that they finish together.
+
+    costs[i] = total work of launch i; units[i] = its number of indivisible tiles (a launch with s CTAs takes
+    ceil(units / s) tile times).  Greedy: every live launch starts with one SM, each further SM goes to the launch
+    that would currently finish last."""
     live = [i for i, c in enumerate(costs) if c > 0]
     shares = [0] * len(costs)
+    if not live:
+        return shares
+    if units is None:
+        units = [max(1, int(round(c))) for c in costs]
+    per_unit = [costs[i] / max(units[i], 1) for i in range(len(costs))]
     for i in live:
-        shares[i] = max(1, int(n_sm * costs[i] / total))
-    while sum(shares) > n_sm:                       # rounding up the small ones may overshoot
-        shares[max(live, key=lambda i: shares[i])] -= 1
-    if live:
-        shares[max(live, key=lambda i: costs[i])] += n_sm - sum(shares)
+        shares[i] = 1
+
+    def finish(i):
+        return -(-units[i] // shares[i]) * per_unit[i]
+
+    for _ in range(max(0, n_sm - len(live))):
+        worst = max(live, key=lambda i: (finish(i), costs[i]))
+        if shares[worst] >= units[worst]:                 # already one CTA per tile: more SMs cannot help it
+            rest = [i for i in live if shares[i] < units[i]]
+            if not rest:
+                break
+            worst = max(rest, key=lambda i: (finish(i), costs[i]))
+        shares[worst] += 1
     return shares
 
 
@@ -289,8 +305,9 @@ class _LayerCombineFn(torch.autograd.Function):
         ch = per[0]["aggs"][0].shape[1]
         need_grad = SAVE_ACTIVATIONS and any(ctx.needs_input_grad)
         n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
-        costs = [float(pr["aggs"][0].shape[0]) * (rc["n_msgs"] + 1) for pr, rc in zip(per, ranks)]
-        shares = _sm_shares(costs, n_sm)
+        tiles = [-(-pr["aggs"][0].shape[0] // 128) for pr in per]
+        costs = [t * (rc["n_msgs"] + 1.2) for t, rc in zip(tiles, ranks)]       # per tile: a fixed part + one part per message
+        shares = _sm_shares(costs, n_sm, tiles)
         outs = []
         for pr, rc in zip(per, ranks):
             rows = pr["aggs"][0].shape[0]
