@@ -445,7 +445,7 @@ __device__ __forceinline__ void same_bwd_body(const DeviceTables& d, const Group
 }
 
 template <int L>
-__global__ void __launch_bounds__(kThreads) agg_same_bwd(const DeviceTables d, const Sections sec,
+__global__ void __launch_bounds__(kThreads, 8) agg_same_bwd(const DeviceTables d, const Sections sec,
                                                          const topo_complex_view cv, const Feat x, const Feat down,
                                                          const Feat up, const Feat g_same, const FeatMut g_down,
                                                          const FeatMut g_up, const FeatMut g_x, float* __restrict__ g_probs) {
