@@ -28,6 +28,7 @@ import torch.nn.functional as F
 
 from ._lib import lib, check, ptr, ptr_array, stream
 from .complex_builder import RANK_KEYS, SparseSimplicialMatrices, build_sparse_matrices
+from . import custom_sccn as _sccn
 from .custom_sccn import BatchedComplex, GradientSCCN
 from .gate import BinaryGumbel, HardConcrete
 from .rectifier import ConstraintMatrices, RectifiedProbs, _Tables, rectify_batch
@@ -79,12 +80,15 @@ class _EmbedFn(torch.autograd.Function):
         lnes = [t.contiguous() for t in (l0, l1, l2, l3)]
         ch = lnes[0].shape[1]
         view = cx.view(probs)
-        outs = []
-        for r in range(4):
-            x = torch.empty(cx.rows_max[r], ch, dtype=torch.float32, device=probs.device)   # live rows are all written
+        outs = [torch.empty(cx.rows_max[r], ch, dtype=torch.float32, device=probs.device) for r in range(4)]   # live rows are all written
+        # the four ranks are independent: largest first on the current stream, the others on side streams
+        forked = _sccn._Forked(probs.device, None) if _sccn.CONCURRENT_RANKS else None
+        for position, r in enumerate((3, 2, 1, 0)):
             if cx.rows_max[r]:
-                check(lib.topo_embed_fwd(cx.tables.handle, C.byref(view), r, ch, ptr(lnes[r]), ptr(x), stream()))
-            outs.append(x)
+                st = forked.stream_for(position) if forked is not None else stream()
+                check(lib.topo_embed_fwd(cx.tables.handle, C.byref(view), r, ch, ptr(lnes[r]), ptr(outs[r]), st))
+        if forked is not None:
+            forked.join()
         ctx.save_for_backward(probs, *lnes)
         ctx.cx, ctx.ch = cx, ch
         return tuple(outs)
@@ -95,15 +99,17 @@ class _EmbedFn(torch.autograd.Function):
         cx, ch = ctx.cx, ctx.ch
         view = cx.view(probs)
         g_probs = torch.zeros_like(probs)
-        g_lnes, keep = [], []
-        for r in range(4):
-            g_l = torch.zeros_like(lnes[r])
-            if g_xs[r] is not None and cx.rows_max[r]:
-                g_x = g_xs[r].contiguous()
-                keep.append(g_x)
-                check(lib.topo_embed_bwd(cx.tables.handle, C.byref(view), r, ch, ptr(lnes[r]), ptr(g_x),
-                                         ptr(g_l), ptr(g_probs), stream()))
-            g_lnes.append(g_l)
+        g_lnes = [torch.zeros_like(lnes[r]) for r in range(4)]
+        keep = [g.contiguous() if g is not None else None for g in g_xs]      # bound to names until the launches are queued
+        # rank r only touches its own slice of g_probs: the four launches run side by side
+        forked = _sccn._Forked(probs.device, None) if _sccn.CONCURRENT_RANKS else None
+        for position, r in enumerate((3, 2, 1, 0)):
+            if keep[r] is not None and cx.rows_max[r]:
+                st = forked.stream_for(position) if forked is not None else stream()
+                check(lib.topo_embed_bwd(cx.tables.handle, C.byref(view), r, ch, ptr(lnes[r]), ptr(keep[r]),
+                                         ptr(g_lnes[r]), ptr(g_probs), st))
+        if forked is not None:
+            forked.join()
         return (None, g_probs, *g_lnes)
 
 
