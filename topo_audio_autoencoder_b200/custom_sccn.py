@@ -399,7 +399,9 @@ class _LayerCombineFn(torch.autograd.Function):
                 arr[q].wprod, arr[q].w, arr[q].scale = ptr(views[i]["wprod"][k]), ptr(pr["ws"][k]), ptr(pr["scales"][k])
                 arr[q].g_w, arr[q].g_scale = g_w_all[q].data_ptr(), g_s_all[q:q + 1].data_ptr()
                 q += 1
-        check(lib.topo_sccn_finish_weight_grads(arr, n_total, ch, stream()))
+        # ... on a side stream: the aggregation backward below does not depend on it
+        tail = _Forked(dev, None)
+        check(lib.topo_sccn_finish_weight_grads(arr, n_total, ch, tail.stream_for(1) if ctx.agg is not None else stream()))
         agg = ctx.agg
         if agg is not None:
             # the aggregation backward runs on this node's own buffers: it updates g_down[2], g_up[2], g_up[3] in
@@ -420,6 +422,7 @@ class _LayerCombineFn(torch.autograd.Function):
             grads_flat[0] = g_probs
             for pr, gx in zip(per, g_x):
                 pr["g_x_total"] = gx
+            tail.join()
         n_agg = 0 if agg is not None else 1
         q = 0
         for i, (pr, rc) in enumerate(zip(per, ranks)):
