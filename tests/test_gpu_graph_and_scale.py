@@ -91,3 +91,53 @@ def test_larger_complex_against_oracle():
                   {k: v.double() for k, v in inc.items()}, {k: v.double() for k, v in adj.items()})
     for r in range(4):
         assert_fp32_equivalent(f"large24/rank_{r}", xs[r], out[f"rank_{r}"], out64[f"rank_{r}"])
+
+
+def test_concurrent_layer_node_equals_the_serial_per_rank_path():
+    """The default execution (one autograd node per layer: aggregation + four rank launches side by side on SM
+    partitions, shared weight images) against the plain path (one node per rank, one launch after another with the
+    whole GPU, images built in-kernel): same kernels, so outputs and input gradients are bit-identical; parameter
+    gradients differ only by the order of their atomic accumulation."""
+    import topo_audio_autoencoder_b200 as T
+    from topo_audio_autoencoder_b200 import custom_sccn as cs
+    n, B, C, L = 12, 4, 64, 3
+    torch.manual_seed(2)
+    stage = T.ComplexStage(n, channels=C, n_layers=L, gate="hard_concrete", bias_on="logits").cuda().train()
+    N = stage.head.total_simplices
+    g = torch.Generator().manual_seed(7)
+    logits = torch.randn(B, N, generator=g).cuda()
+    noise = torch.rand(B, N, generator=g).clamp_(1e-6, 1 - 1e-6).cuda()
+    counts = stage.head._tables.counts
+    ups = [torch.randn(B * c, C, generator=g).cuda() for c in counts] + [torch.ones(B).cuda(), torch.ones(B).cuda()]
+    params = [p for p in stage.parameters() if p.requires_grad]
+
+    def run():
+        for p in params:
+            p.grad = None
+        lg = logits.clone().requires_grad_(True)
+        out = stage(lg, noise)
+        heads = [out[f"rank_{r}"] for r in range(4)] + [out["vertex_penalty"], out["entropy_loss"]]
+        torch.autograd.backward(heads, ups)
+        torch.cuda.synchronize()
+        live = out["complex"].row_off[:, B].tolist()
+        return ([out[f"rank_{r}"][:live[r]].clone() for r in range(4)], lg.grad.clone(),
+                [None if p.grad is None else p.grad.clone() for p in params])
+
+    saved = (cs.CONCURRENT_RANKS, cs.SHARED_WEIGHT_IMAGES)
+    try:
+        cs.CONCURRENT_RANKS, cs.SHARED_WEIGHT_IMAGES = True, True
+        outs_c, lg_c, grads_c = run()
+        cs.CONCURRENT_RANKS, cs.SHARED_WEIGHT_IMAGES = False, False
+        outs_s, lg_s, grads_s = run()
+    finally:
+        cs.CONCURRENT_RANKS, cs.SHARED_WEIGHT_IMAGES = saved
+    for r in range(4):
+        # V_k = s_k W_k W1^T is formed by different code in the two modes (weight_images.cu vs in-kernel): same formula,
+        # same order of operations
+        assert_close(f"paths/out{r}", outs_c[r], outs_s[r], rtol=1e-6, atol=1e-6)
+    assert_close("paths/logits-grad", lg_c, lg_s, rtol=1e-5, atol=1e-6 * max(1.0, lg_s.abs().max().item()))
+    for gc, gs in zip(grads_c, grads_s):
+        if gc is None or gs is None:
+            assert gc is None and gs is None
+            continue
+        assert_close("paths/param-grad", gc, gs, rtol=1e-4, atol=1e-4 * max(1.0, gs.abs().max().item()))
