@@ -346,6 +346,8 @@ int topo_debug_gemm_tf32x3(const float* a, const float* w, int64_t rows, int mod
  *   mode 0: out[rows, 64] = a @ w     (w stored [in][out], read MN-major)
  *   mode 1: out[rows, 64] = a @ w^T   (w stored [out][in], read K-major)
  *   mode 2: out[64, 64]  += a^T w     (w is a second [rows, 64] matrix; both read MN-major, contraction over rows)
+ *   mode 3: layout probe (where the rows of an M = 64 accumulator land in tensor memory)
+ *   mode 4: mode 1 issued as tcgen05.mma.cta_group::2 by clusters of two CTAs that each hold half of the weight image
  * mn_lbo / mn_sbo / mn_kstep: descriptor fields of the MN-major operands in bytes (16384 / 1024 / 2048 for
  * the layouts in tc16.cuh; exposed so the test can pin them). */
 int topo_debug_gemm_bf16x3(const float* a, const float* w, int64_t rows, int mode, int mn_lbo, int mn_sbo,

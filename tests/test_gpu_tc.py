@@ -334,3 +334,23 @@ def test_second_generation_forward_and_its_backward(n_msgs, apply_ln, rows, resi
         if name == "b2":      # softmax is shift invariant: the exact gradient is 0 and both values are pure round-off
             tol = 1e-4
         assert (a_ - b_).abs().max().item() <= tol, (name, (a_ - b_).abs().max().item(), tol)
+
+
+@pytest.mark.parametrize("rows", [128, 256, 1000, 20000])
+def test_cta_pair_gemm_shares_the_weight_image(rows):
+    """mode 4: tcgen05.mma.cta_group::2 issued by clusters of two CTAs, each holding its own 128-row operand tile and
+    HALF of the weight image (M = 256 product, 128 accumulator rows per CTA): remote mbarrier arrival, multicast commit,
+    cta_group::2 tensor-memory allocation -- the primitive for halving the resident weight images of the combine kernels."""
+    from topo_audio_autoencoder_b200._lib import lib, check, ptr, stream
+    g = torch.Generator().manual_seed(rows + 4)
+    a = (torch.randn(rows, 64, generator=g) * torch.logspace(-3, 3, 64)).cuda()
+    w = torch.randn(64, 64, generator=g).cuda()
+    out = torch.full((rows, 64), float("nan"), device="cuda")
+    check(lib.topo_debug_gemm_bf16x3(ptr(a), ptr(w), rows, 4, 0, 0, 0, ptr(out), stream()))
+    torch.cuda.synchronize()
+    want = a.double() @ w.double().t()
+    cond = a.double().abs() @ w.double().abs().t()
+    err = ((out.double() - want).abs() / cond).max().item()
+    report(f"tc/gemm-bf16x3/cta-pair/rows={rows}", out, want.float())
+    assert torch.isfinite(out).all()
+    assert err < 5e-7, f"relative-to-condition error {err:.3e}"
