@@ -73,8 +73,8 @@ __device__ __forceinline__ void load_chunk(const float* __restrict__ src, long l
     float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
     if (ok) {
         const float4* p = reinterpret_cast<const float4*>(src + row * kC) + chunk * 2;
-        a = __ldg(p);
-        b = __ldg(p + 1);
+        a = ldg_pinned(p);            // issued where written: these are prefetches into registers
+        b = ldg_pinned(p + 1);
     }
     v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
 }
@@ -89,8 +89,8 @@ __device__ __forceinline__ void load_saved(const float* __restrict__ src, bool t
     float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
     if (ok) {
         const float4* p = reinterpret_cast<const float4*>(src) + tf_index_chunk(row0, tile_row, chunk);
-        a = __ldg(p);
-        b = __ldg(p + kTileRows);
+        a = ldg_pinned(p);
+        b = ldg_pinned(p + kTileRows);
     }
     v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
 }
@@ -231,6 +231,23 @@ __global__ void __launch_bounds__(kThreads, 1) combine_bwd_fused_kernel(topo_com
 #pragma unroll
     for (int i = 0; i < 8; ++i) p_b1[i] = p_w2[i] = p_gamma[i] = p_beta[i] = 0.f;
 
+    // phase-A operands of the NEXT tile are loaded before the current tile's last MMA round is awaited
+    float n_dy[2][8], n_mk[3][2][8], n_sc[2][3];
+    auto load_phase_a = [&](long long t) {
+        const long long r0 = t * kTileRows;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const long long gr = r0 + ra + 64 * j;
+            const bool ok = t < tiles && gr < live;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) n_sc[j][k] = (k < n_msgs && ok) ? __ldg(P.saved_score + k * rows + gr) : 0.f;
+            load_chunk(grad_out, gr, c, ok, n_dy[j]);
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+                if (k < n_msgs) load_saved(P.saved_m[k], tf, r0, ra + 64 * j, c, ok, n_mk[k][j]);
+        }
+    };
+    load_phase_a(blockIdx.x);
     for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++tiles_done) {
         const long long row0 = tile * kTileRows;
         const long long grow[2] = {row0 + ra, row0 + ra + 64};
@@ -245,11 +262,16 @@ __global__ void __launch_bounds__(kThreads, 1) combine_bwd_fused_kernel(topo_com
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
 #pragma unroll
-                for (int k = 0; k < 3; ++k) sc[j][k] = (k < n_msgs && alive[j]) ? __ldg(P.saved_score + k * rows + grow[j]) : 0.f;
-                load_chunk(grad_out, grow[j], c, alive[j], dy[j]);
+                for (int k = 0; k < 3; ++k) sc[j][k] = n_sc[j][k];
 #pragma unroll
-                for (int k = 0; k < 3; ++k)
-                    if (k < n_msgs) load_saved(P.saved_m[k], tf, row0, ra + 64 * j, c, alive[j], mk[k][j]);
+                for (int i = 0; i < 8; ++i) dy[j][i] = n_dy[j][i];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    if (k < n_msgs) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) mk[k][j][i] = n_mk[k][j][i];
+                    }
+                }
             }
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
@@ -467,6 +489,11 @@ __global__ void __launch_bounds__(kThreads, 1) combine_bwd_fused_kernel(topo_com
                 }
                 store_split8(p_img, kPart, r, 2 * q, lo);
                 store_split8(p_img, kPart, r, 2 * q + 1, hi);
+                if (k == n_msgs - 1 && row_alive && G.g_x != nullptr) {       // g_x = sum_k dm_k is complete here
+                    float4* dxp = reinterpret_cast<float4*>(G.g_x + row * kC + col0);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) dxp[i] = make_float4(dx[4 * i], dx[4 * i + 1], dx[4 * i + 2], dx[4 * i + 3]);
+                }
             }
 #pragma unroll
             for (int j = 0; j < 2; ++j) store_split8(q_img, kPart, ra + 64 * j, c, ag[j]);
@@ -492,8 +519,9 @@ __global__ void __launch_bounds__(kThreads, 1) combine_bwd_fused_kernel(topo_com
                 for (int j = 0; j < 2; ++j) load_saved(P.saved_pre[k + 1], tf, row0, ra + 64 * j, c, alive[j], pre[j]);
             }
         }
-        // round 2 of the last message
+        // round 2 of the last message: the next tile's phase-A operands start moving before it is awaited
         stamp();                                               // last round 2 issued
+        load_phase_a(tile + gridDim.x);
         mbar_wait_backoff(bar, parity);
         parity ^= 1;
         tc_fence_after_sync();
@@ -506,11 +534,6 @@ __global__ void __launch_bounds__(kThreads, 1) combine_bwd_fused_kernel(topo_com
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
                     dst[i] = make_float4(sp * ga[4 * i], sp * ga[4 * i + 1], sp * ga[4 * i + 2], sp * ga[4 * i + 3]);
-                if (G.g_x != nullptr) {
-                    float4* dxp = reinterpret_cast<float4*>(G.g_x + row * kC + col0);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) dxp[i] = make_float4(dx[4 * i], dx[4 * i + 1], dx[4 * i + 2], dx[4 * i + 3]);
-                }
             }
         }
         tc_fence_before_sync();
