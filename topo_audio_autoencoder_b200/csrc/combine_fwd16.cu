@@ -383,18 +383,29 @@ __global__ void __launch_bounds__(kThreads, 1) combine_fwd16_kernel(topo_combine
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
             if (k < n_msgs) {
-                // this thread wrote exactly these addresses a moment ago (same thread, program order)
-                const float4* pm = reinterpret_cast<const float4*>(P.saved_m[k]) + tf_index(row0, q, r);
+                if (k + 2 >= n_msgs) {
+                    // the last two messages' products are still in tensor memory (buffer k & 1 is only overwritten by
+                    // message k + 2): m_k = s_k D1_k + x again, without a trip to L2
+                    float d1[kCW];
+                    tmem_ld16(tmem_base + (k & 1) * 128 + lane_addr + col0, d1);
+                    const float sk = k == 0 ? scale_r[0] : (k == 1 ? scale_r[1] : scale_r[2]);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float4 t = (row_alive && !(dbg & 32)) ? pm[j * kTileRows] : make_float4(0.f, 0.f, 0.f, 0.f);
-                    y[4 * j] = fmaf(att[k], t.x, y[4 * j]);
-                    y[4 * j + 1] = fmaf(att[k], t.y, y[4 * j + 1]);
-                    y[4 * j + 2] = fmaf(att[k], t.z, y[4 * j + 2]);
-                    y[4 * j + 3] = fmaf(att[k], t.w, y[4 * j + 3]);
+                    for (int i = 0; i < kCW; ++i) y[i] = fmaf(att[k], fmaf(sk, d1[i], xr[i]), y[i]);
+                } else {
+                    // this thread wrote exactly these addresses a moment ago (same thread, program order)
+                    const float4* pm = reinterpret_cast<const float4*>(P.saved_m[k]) + tf_index(row0, q, r);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float4 t = (row_alive && !(dbg & 32)) ? pm[j * kTileRows] : make_float4(0.f, 0.f, 0.f, 0.f);
+                        y[4 * j] = fmaf(att[k], t.x, y[4 * j]);
+                        y[4 * j + 1] = fmaf(att[k], t.y, y[4 * j + 1]);
+                        y[4 * j + 2] = fmaf(att[k], t.z, y[4 * j + 2]);
+                        y[4 * j + 3] = fmaf(att[k], t.w, y[4 * j + 3]);
+                    }
                 }
             }
         }
+        tc_fence_before_sync();
         if (P.apply_ln) {
             float part = 0.f;
 #pragma unroll
