@@ -353,6 +353,14 @@ int topo_debug_gemm_tf32x3(const float* a, const float* w, int64_t rows, int mod
 int topo_debug_gemm_bf16x3(const float* a, const float* w, int64_t rows, int mode, int mn_lbo, int mn_sbo,
                            int mn_kstep, float* out, topo_stream_t stream);
 
+/* Measurement hooks of the two tensor-core combine kernels (scripts/ablate_fwd16.py, scripts/ablate_bwd.py).  They only
+ * act in a library built with TOPO_DEBUG_KERNELS=1; the shipped build ignores them.
+ *   mask:   bit set = one part of the forward switched off for differential timing (results are then wrong)
+ *   stamps: device buffer of uint64 that CTA 0 / thread 0 fills with %globaltimer values at phase boundaries */
+void topo_debug_fwd16_mask(int mask);
+void topo_debug_fwd16_stamps(unsigned long long* device_buffer);
+void topo_debug_bwd_stamps(unsigned long long* device_buffer);
+
 /* ---------------------------------------------------------------------------------------------
  * D1-D3. Tiled pairwise spectral distance.  Replaces the pair loop of compute_distances
  * (precompute_distances.py:89-115) and BatchAudioDistance.forward (:33-49) on precomputed

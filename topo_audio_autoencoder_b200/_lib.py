@@ -105,11 +105,15 @@ SIGNATURES = {
     "topo_sccn_combine_bwd_tc": [C.POINTER(CombineParams), _I64, _P, _P, C.POINTER(CombineGrads), _P],
     "topo_debug_gemm_tf32x3": [_P, _P, _I64, _I32, _P, _P],
     "topo_debug_gemm_bf16x3": [_P, _P, _I64, _I32, _I32, _I32, _I32, _P, _P],
+    "topo_debug_fwd16_mask": [_I32],
+    "topo_debug_fwd16_stamps": [_P],
+    "topo_debug_bwd_stamps": [_P],
     "topo_distance_padded_size": [C.POINTER(_I64), _I32],
     "topo_distance_prepare": [_P, _I64, _I64, C.POINTER(_I64), _I32, _F, _P, _P, _P, _P],
     "topo_distance_rows": [_P, _P, _P, _I64, C.POINTER(_I64), _I32, _I64, _I64, _I64, _I64, _P, _P],
 }
 _NON_STATUS = {"topo_version": C.c_int, "topo_last_error": C.c_char_p, "topo_tables_destroy": None,
+               "topo_debug_fwd16_mask": None, "topo_debug_fwd16_stamps": None, "topo_debug_bwd_stamps": None,
                "topo_distance_padded_size": C.c_int64}
 
 
