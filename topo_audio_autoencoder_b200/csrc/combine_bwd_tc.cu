@@ -113,7 +113,6 @@ __device__ __forceinline__ void row_sum8_pair(float& a, float& b) {
     }
 }
 
-__device__ __forceinline__ void prefetch_l2_line(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 __device__ __forceinline__ uint32_t dy_off(int row, int c16 /* 0..15 */) {
     return static_cast<uint32_t>(row * 256 + ((c16 ^ (row & 7)) << 4));
@@ -411,14 +410,18 @@ __global__ void __launch_bounds__(kThreads, 1) combine_bwd_fused_kernel(topo_com
             for (int j = 0; j < 2; ++j) {
                 const float dsk = k == 0 ? dsc[j][0] : (k == 1 ? dsc[j][1] : dsc[j][2]);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const float x = pre[j][i];
-                    float cdf, pdf;
-                    gelu_cdf_pdf(x, cdf, pdf);
-                    p_w2[i] = fmaf(dsk, x * cdf, p_w2[i]);                    // dscore_k GELU(pre): w2 gradient
-                    const float d = dsk * w2c[i] * (cdf + x * pdf);           // dpre_k
-                    p_b1[i] += d;
-                    pre[j][i] = d;
+                for (int i0 = 0; i0 < 8; i0 += 4) {
+                    float cdf[4], pdf[4];
+                    gelu_cdf_pdf_n<4>(pre[j] + i0, cdf, pdf);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int i = i0 + e;
+                        const float x = pre[j][i];
+                        p_w2[i] = fmaf(dsk, x * cdf[e], p_w2[i]);             // dscore_k GELU(pre): w2 gradient
+                        const float d = dsk * w2c[i] * (cdf[e] + x * pdf[e]); // dpre_k
+                        p_b1[i] += d;
+                        pre[j][i] = d;
+                    }
                 }
             }
             if (k > 0) {

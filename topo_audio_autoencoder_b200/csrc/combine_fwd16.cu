@@ -261,31 +261,29 @@ __global__ void __launch_bounds__(kThreads, 1) combine_fwd16_kernel(topo_combine
     }
     int slot = 0;                   // slot of the unit being staged (runs on across tiles)
     uint32_t unit_no = 0;
-    float xn[kCW];                  // the next tile's residual slice
-    {
-        const long long nrow = static_cast<long long>(blockIdx.x) * kTileRows + r;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (has_x && nrow < live && !(dbg & 256)) t = ldg_pinned(reinterpret_cast<const float4*>(P.x + nrow * kC + col0) + j);
-            xn[4 * j] = t.x; xn[4 * j + 1] = t.y; xn[4 * j + 2] = t.z; xn[4 * j + 3] = t.w;
-        }
-    }
     for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
         const long long row0 = tile * kTileRows;
         const long long row = row0 + r;
         const bool row_alive = row < live;
-        float xr[kCW];              // row map: this thread's slice of the residual row (loaded one tile ahead)
-#pragma unroll
-        for (int i = 0; i < kCW; ++i) xr[i] = xn[i];
+        // every line this CTA reads for its next tile goes to L2 now, a whole tile ahead of the register loads
         {
-            const long long nrow = (tile + gridDim.x) * kTileRows + r;
+            const long long prow0 = (tile + gridDim.x) * kTileRows;
+            if ((c & 3) == 0 && !(dbg & 8)) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (has_x && nrow < live && !(dbg & 256)) t = ldg_pinned(reinterpret_cast<const float4*>(P.x + nrow * kC + col0) + j);
-                xn[4 * j] = t.x; xn[4 * j + 1] = t.y; xn[4 * j + 2] = t.z; xn[4 * j + 3] = t.w;
+                for (int j = 0; j < 2; ++j) {
+                    const long long prow = prow0 + ra + 64 * j;
+                    if (prow < live) {
+                        for (int u = 0; u < n_units; ++u) prefetch_l2_line(unit_src(u) + prow * kC + 8 * c);
+                    }
+                }
             }
+        }
+        float xr[kCW];              // row map: this thread's slice of the residual row (in L2 since the previous tile)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (has_x && row_alive && !(dbg & 256)) t = ldg_pinned(reinterpret_cast<const float4*>(P.x + row * kC + col0) + j);
+            xr[4 * j] = t.x; xr[4 * j + 1] = t.y; xr[4 * j + 2] = t.z; xr[4 * j + 3] = t.w;
         }
         int prev_slot = 0;
 #pragma unroll 1
@@ -318,13 +316,29 @@ __global__ void __launch_bounds__(kThreads, 1) combine_fwd16_kernel(topo_combine
                 if (k >= 0) {
                     const uint32_t tm = tmem_base + (k & 1) * 128 + lane_addr + col0;
                     const float sk = k == 0 ? scale_r[0] : (k == 1 ? scale_r[1] : scale_r[2]);
-                    float m[kCW], h[kCW];
+                    // the message first, so that its registers are free again before the GELU evaluations need theirs
+                    {
+                        float m[kCW];
+                        if (!(dbg & 64)) {
+                            tmem_ld16(tm, m);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < kCW; ++i) m[i] = 0.01f * i;
+                        }
+#pragma unroll
+                        for (int i = 0; i < kCW; ++i) m[i] = fmaf(sk, m[i], xr[i]);
+                        float4* pm = reinterpret_cast<float4*>(P.saved_m[k]) + tf_index(row0, q, r);
+                        if (row_alive && !(dbg & 1)) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) pm[j * kTileRows] = make_float4(m[4 * j], m[4 * j + 1], m[4 * j + 2], m[4 * j + 3]);
+                        }
+                    }
+                    float h[kCW];
                     if (!(dbg & 64)) {
-                        tmem_ld16(tm, m);
                         tmem_ld16(tm + 64, h);
                     } else {
 #pragma unroll
-                        for (int i = 0; i < kCW; ++i) m[i] = h[i] = 0.01f * i;
+                        for (int i = 0; i < kCW; ++i) h[i] = 0.01f * i;
                     }
                     if (has_x && !(dbg & 64)) {
                         float h0[kCW];
@@ -332,23 +346,22 @@ __global__ void __launch_bounds__(kThreads, 1) combine_fwd16_kernel(topo_combine
 #pragma unroll
                         for (int i = 0; i < kCW; ++i) h[i] += h0[i];
                     }
-                    float part = 0.f;
 #pragma unroll
-                    for (int i = 0; i < kCW; ++i) {
-                        m[i] = fmaf(sk, m[i], xr[i]);                              // the message
-                        h[i] += vecs[col0 + i];                                    // pre-GELU hidden activation
-                        part = fmaf((dbg & 2) ? h[i] : gelu_fast_exact(h[i]), vecs[kC + col0 + i], part);
-                    }
-                    red[(k * 4 + q) * kTileRows + r] = part;
-                    float4* pm = reinterpret_cast<float4*>(P.saved_m[k]) + tf_index(row0, q, r);
+                    for (int i = 0; i < kCW; ++i) h[i] += vecs[col0 + i];          // pre-GELU hidden activation
                     float4* pp = reinterpret_cast<float4*>(P.saved_pre[k]) + tf_index(row0, q, r);
                     if (row_alive && !(dbg & 1)) {
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            pm[j * kTileRows] = make_float4(m[4 * j], m[4 * j + 1], m[4 * j + 2], m[4 * j + 3]);
-                            pp[j * kTileRows] = make_float4(h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]);
-                        }
+                        for (int j = 0; j < 4; ++j) pp[j * kTileRows] = make_float4(h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]);
                     }
+                    float part = 0.f;
+#pragma unroll
+                    for (int i = 0; i < kCW; i += 4) {
+                        float cdf[4], pdf[4];
+                        gelu_cdf_pdf_n<4>(h + i, cdf, pdf);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) part = fmaf((dbg & 2) ? h[i + e] : h[i + e] * cdf[e], vecs[kC + col0 + i + e], part);
+                    }
+                    red[(k * 4 + q) * kTileRows + r] = part;
                 }
                 tc_fence_before_sync();
             }

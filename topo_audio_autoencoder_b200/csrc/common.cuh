@@ -110,8 +110,9 @@ __device__ __forceinline__ void gelu_cdf_pdf(float x, float& cdf, float& pdf) {
     p = fmaf(p, t, 0.21989449846757936f);
     p = fmaf(p, t, 0.23661221813005356f);
     p = fmaf(p, t, 0.23697332130814744f);
-    const float e = __expf(-0.5f * x * x);
-    const float hq = 0.5f * t * p * e;                 // erfc(|x| / sqrt 2) / 2 = Phi(-|x|)
+    float e;                                           // exp(-x^2/2) = 2^(x * (x * -log2(e)/2)); flush-to-zero form: one MUFU
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * (x * -0.72134752044448170368f)));
+    const float hq = (0.5f * t) * p * e;               // erfc(|x| / sqrt 2) / 2 = Phi(-|x|)
     cdf = x >= 0.0f ? 1.0f - hq : hq;
     pdf = 0.39894228040143267794f * e;
 }
@@ -119,6 +120,33 @@ __device__ __forceinline__ float gelu_fast_exact(float x) {
     float cdf, pdf;
     gelu_cdf_pdf(x, cdf, pdf);
     return x * cdf;
+}
+// N independent evaluations written stage by stage: ptxas keeps a single evaluation as one dependent chain
+// (about twenty instructions at four cycles each), so the interleaving has to be in the source.
+template <int N>
+__device__ __forceinline__ void gelu_cdf_pdf_n(const float* x, float* cdf, float* pdf) {
+    float t[N], p[N], e[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t[i]) : "f"(fmaf(fabsf(x[i]), 0.42f * 0.70710678118654752440f, 1.0f)));
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e[i]) : "f"(x[i] * (x[i] * -0.72134752044448170368f)));
+#pragma unroll
+    for (int i = 0; i < N; ++i) p[i] = fmaf(-0.04113744501622546f, t[i], 0.23070530236756076f);
+    constexpr float kCoef[8] = {-0.4866430497963537f, 0.437150493790159f, -0.19732979111351331f, 0.2137338489469954f,
+                                0.150040600633153f, 0.21989449846757936f, 0.23661221813005356f, 0.23697332130814744f};
+#pragma unroll
+    for (int s = 0; s < 8; ++s) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) p[i] = fmaf(p[i], t[i], kCoef[s]);
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        const float hq = (0.5f * t[i]) * p[i] * e[i];
+        cdf[i] = x[i] >= 0.0f ? 1.0f - hq : hq;
+        pdf[i] = 0.39894228040143267794f * e[i];
+    }
 }
 
 template <int VEC>

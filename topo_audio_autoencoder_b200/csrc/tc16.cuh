@@ -45,10 +45,11 @@ __device__ __forceinline__ uint32_t img_off(int row, int chunk /* 0..7 */) {
 }
 
 __device__ __forceinline__ uint32_t pack2(float a, float b, float& ra, float& rb) {
-    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);       // .x = a -> low half -> lower address
-    ra = a - __low2float(h);
-    rb = b - __high2float(h);
-    return *reinterpret_cast<const uint32_t*>(&h);
+    uint32_t h;                                                 // a -> low half -> lower address
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(b), "f"(a));
+    ra = a - __uint_as_float(h << 16);                          // a bf16 is the upper half of its float
+    rb = b - __uint_as_float(h & 0xffff0000u);
+    return h;
 }
 
 // eight consecutive columns -> one 16-byte chunk in each of the three parts
@@ -127,6 +128,8 @@ __device__ __forceinline__ void gemm_bf16x3_unrolled(uint32_t tmem_d, const Oper
 __device__ __forceinline__ void prefetch_l2(const void* p, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
+
+__device__ __forceinline__ void prefetch_l2_line(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 }  // namespace tc16
 }  // namespace topo
