@@ -46,9 +46,9 @@ struct FwdSmem16 {
     static constexpr uint32_t kW1 = kImg;                 // W1 [o][i]
     static constexpr uint32_t kWV = kW1 + kWImg;          // per message: W_k [in][out] then V_k [in][hidden] (48 KB)
     static constexpr uint32_t kA1 = kWV + 2 * 2 * kWImg;  // operand slot 1 = the third message's weights (n_msgs < 3 only)
-    static constexpr uint32_t kVec = kWV + 3 * 2 * kWImg; // b1, w2, gamma, beta
-    static constexpr uint32_t kRed = kVec + 4 * kC * 4;   // [4 slots][4 column groups][128 rows]
-    static constexpr uint32_t kBar = kRed + 4 * 4 * kTileRows * 4;
+    static constexpr uint32_t kVec = kWV + 3 * 2 * kWImg; // b1, w2
+    static constexpr uint32_t kRed = kVec + 2 * kC * 4;   // [3 score slots + sum + squared deviations][4 column groups][128 rows]
+    static constexpr uint32_t kBar = kRed + 5 * 4 * kTileRows * 4;
     static constexpr uint32_t kTotal = kBar + 32;
 };
 static_assert(FwdSmem16::kA1 % 1024 == 0 && FwdSmem16::kTotal <= 232448, "shared-memory layout");
@@ -190,8 +190,6 @@ __global__ void __launch_bounds__(kThreads, 1) combine_fwd16_kernel(topo_combine
     for (int i = tid; i < kC; i += kThreads) {
         vecs[i] = __ldg(P.att_b1 + i);
         vecs[kC + i] = __ldg(P.att_w2 + i);
-        vecs[2 * kC + i] = P.apply_ln ? __ldg(P.ln_gamma + i) : 1.f;
-        vecs[3 * kC + i] = P.apply_ln ? __ldg(P.ln_beta + i) : 0.f;
     }
     stamp(1);
     fence_async_shared();
@@ -420,28 +418,50 @@ __global__ void __launch_bounds__(kThreads, 1) combine_fwd16_kernel(topo_combine
         }
         tc_fence_before_sync();
         if (P.apply_ln) {
+            // Row statistics with ONE exchange: every thread reduces its 16 columns to (sum, squared deviations from
+            // its own mean) and the four partials of a row are merged exactly (Chan et al.): no E[y^2] - mean^2.
             float part = 0.f;
 #pragma unroll
             for (int i = 0; i < kCW; ++i) part += y[i];
+            const float lmean = part * (1.0f / kCW);
+            float dev = 0.f;
+#pragma unroll
+            for (int i = 0; i < kCW; ++i) dev = fmaf(y[i] - lmean, y[i] - lmean, dev);
             red[(3 * 4 + q) * kTileRows + r] = part;
-            named_bar_sync(3, kWorkers);
-            const float* rm = red + 3 * 4 * kTileRows;
-            const float mean = ((rm[r] + rm[kTileRows + r]) + (rm[2 * kTileRows + r] + rm[3 * kTileRows + r])) * (1.0f / kC);
-            float var = 0.f;
+            red[(4 * 4 + q) * kTileRows + r] = dev;
+            float4 gm[4], bt[4];                           // gamma / beta: 64 floats, L1 resident
 #pragma unroll
-            for (int i = 0; i < kCW; ++i) var = fmaf(y[i] - mean, y[i] - mean, var);
-            red[q * kTileRows + r] = var;                  // slot 0: every thread is past its score reads
+            for (int j = 0; j < 4; ++j) {
+                gm[j] = __ldg(reinterpret_cast<const float4*>(P.ln_gamma + col0) + j);
+                bt[j] = __ldg(reinterpret_cast<const float4*>(P.ln_beta + col0) + j);
+            }
             named_bar_sync(3, kWorkers);
-            const float rstd = 1.0f / sqrtf(((red[r] + red[kTileRows + r]) + (red[2 * kTileRows + r] + red[3 * kTileRows + r])) * (1.0f / kC) + P.ln_eps);
+            const float* rs = red + 3 * 4 * kTileRows;
+            const float* rd = red + 4 * 4 * kTileRows;
+            const float s0 = rs[r], s1 = rs[kTileRows + r], s2 = rs[2 * kTileRows + r], s3 = rs[3 * kTileRows + r];
+            const float mean = ((s0 + s1) + (s2 + s3)) * (1.0f / kC);
+            const float d0 = s0 * (1.0f / kCW) - mean, d1 = s1 * (1.0f / kCW) - mean, d2 = s2 * (1.0f / kCW) - mean, d3 = s3 * (1.0f / kCW) - mean;
+            const float m2 = ((rd[r] + rd[kTileRows + r]) + (rd[2 * kTileRows + r] + rd[3 * kTileRows + r])) +
+                             static_cast<float>(kCW) * ((d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3));
+            const float rstd = 1.0f / sqrtf(m2 * (1.0f / kC) + P.ln_eps);
 #pragma unroll
-            for (int i = 0; i < kCW; ++i) y[i] = fmaf((y[i] - mean) * rstd, vecs[2 * kC + col0 + i], vecs[3 * kC + col0 + i]);
+            for (int j = 0; j < 4; ++j) {
+                y[4 * j] = fmaf((y[4 * j] - mean) * rstd, gm[j].x, bt[j].x);
+                y[4 * j + 1] = fmaf((y[4 * j + 1] - mean) * rstd, gm[j].y, bt[j].y);
+                y[4 * j + 2] = fmaf((y[4 * j + 2] - mean) * rstd, gm[j].z, bt[j].z);
+                y[4 * j + 3] = fmaf((y[4 * j + 3] - mean) * rstd, gm[j].w, bt[j].w);
+            }
+        }
+        else {
+            named_bar_sync(3, kWorkers);                   // without the exchange: the score slots must be read by everyone
         }
         if (row_alive && !(dbg & 32)) {
             float4* dst = reinterpret_cast<float4*>(out + row * kC + col0);
 #pragma unroll
             for (int j = 0; j < 4; ++j) dst[j] = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
         }
-        named_bar_sync(3, kWorkers);                       // `red` is rewritten by the next tile's epilogues
+        // no barrier here: the score slots are not read after the exchange above, and the statistics slots are next
+        // written behind the next tile's score barrier, which no thread passes before it has read them
         if (tile == blockIdx.x) stamp(4);
     }
     }   // workers
