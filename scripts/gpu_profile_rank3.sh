@@ -1,0 +1,10 @@
+# ncu --set full of the rank-3 launch (78 % of the rows) of the fused backward and of the forward, whole GPU each
+set -x
+mkdir -p gpurun_out
+export TOPO_CONCURRENT_RANKS=0
+CMD="python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-profile-pass --no-graph"
+$CMD > gpurun_out/plain2.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:combine_bwd_fused -s 0 -c 1 -f -o gpurun_out/prof_bwd_r3 $CMD > gpurun_out/ncu_bwd.log 2>&1
+echo "exit bwd: $?"
+ncu --set full --clock-control none --import-source on -k regex:combine_fwd16 -s 3 -c 1 -f -o gpurun_out/prof_fwd_r3 $CMD > gpurun_out/ncu_fwd.log 2>&1
+echo "exit fwd: $?"

@@ -114,6 +114,10 @@ __device__ __forceinline__ void row_sum8_pair(float& a, float& b) {
 }
 
 
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 __device__ __forceinline__ uint32_t dy_off(int row, int c16 /* 0..15 */) {
     return static_cast<uint32_t>(row * 256 + ((c16 ^ (row & 7)) << 4));
 }
@@ -255,7 +259,7 @@ __global__ void __launch_bounds__(kThreads, 1) combine_bwd_fused_kernel(topo_com
         // ---------------- phase A (chunk map): softmax weights, LayerNorm backward, dscore ----------------
         // Both rows of the thread advance together (every statement is written for j = 0, 1) so that their
         // dependent chains -- loads, row reductions, exp, rsqrt -- overlap instead of running back to back.
-        float dy[2][8], dsc[2][3];
+        float dy[2][8], dsc[2][3], pre[2][8];
         {
             float mk[3][2][8], att[2][3], sc[2][3];
 #pragma unroll
@@ -336,6 +340,9 @@ __global__ void __launch_bounds__(kThreads, 1) combine_bwd_fused_kernel(topo_com
                     for (int i = 0; i < 8; ++i) dy[j][i] = rstd[j] * (dy[j][i] * gmc[i] - c1[j] - y[j][i] * c2[j]);
                 }
             }
+            // the first message's hidden pre-activations: issued here, used right after phase A
+#pragma unroll
+            for (int j = 0; j < 2; ++j) load_saved(P.saved_pre[0], tf, row0, ra + 64 * j, c, alive[j], pre[j]);
             // dscore_k = a_k (dy . m_k - sum_j a_j dy . m_j)
             float da[2][3];
 #pragma unroll
@@ -395,9 +402,6 @@ __global__ void __launch_bounds__(kThreads, 1) combine_bwd_fused_kernel(topo_com
         for (int i = 0; i < kCW; ++i) dx[i] = 0.f;
         const long long row = row0 + r;                                       // row map
         const bool row_alive = row < live;
-        float pre[2][8];
-#pragma unroll
-        for (int j = 0; j < 2; ++j) load_saved(P.saved_pre[0], tf, row0, ra + 64 * j, c, alive[j], pre[j]);
 #pragma unroll 1
         for (int k = 0; k < n_msgs; ++k) {
             float mq[2][8];
@@ -466,20 +470,25 @@ __global__ void __launch_bounds__(kThreads, 1) combine_bwd_fused_kernel(topo_com
             float ag[2][8];
 #pragma unroll
             for (int j = 0; j < 2; ++j) load_chunk(P.agg[k], grow[j], c, alive[j], ag[j]);
-            // the row map's view of dy and a_k
-            float t[kCW];
+            // the next message's hidden pre-activations travel while this round runs (their image is staged: `pre` is free)
+            if (k + 1 < n_msgs) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float4 v = *reinterpret_cast<const float4*>(dy_s + dy_off(r, 4 * q + i));
-                t[4 * i] = v.x; t[4 * i + 1] = v.y; t[4 * i + 2] = v.z; t[4 * i + 3] = v.w;
+                for (int j = 0; j < 2; ++j) load_saved(P.saved_pre[k + 1], tf, row0, ra + 64 * j, c, alive[j], pre[j]);
             }
-            const float ak = att_s[k * kTileRows + r];
             stamp();                                           // round 1 issued, agg loads issued
             mbar_wait_backoff(bar, parity);
             parity ^= 1;
             tc_fence_after_sync();
             stamp();                                           // round 1 complete
             {
+                // the row map's view of dy and a_k
+                float t[kCW];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float4 v = *reinterpret_cast<const float4*>(dy_s + dy_off(r, 4 * q + i));
+                    t[4 * i] = v.x; t[4 * i + 1] = v.y; t[4 * i + 2] = v.z; t[4 * i + 3] = v.w;
+                }
+                const float ak = att_s[k * kTileRows + r];
                 float tt[kCW];
                 tmem_ld16(tm_t + lane_addr + col0, tt);
                 float lo[8], hi[8];
@@ -516,10 +525,6 @@ __global__ void __launch_bounds__(kThreads, 1) combine_bwd_fused_kernel(topo_com
                     mma_commit(bar);
                 }
                 __syncwarp();
-            }
-            if (k + 1 < n_msgs) {
-#pragma unroll
-                for (int j = 0; j < 2; ++j) load_saved(P.saved_pre[k + 1], tf, row0, ra + 64 * j, c, alive[j], pre[j]);
             }
         }
         // round 2 of the last message: the next tile's phase-A operands start moving before it is awaited
@@ -589,14 +594,21 @@ __global__ void __launch_bounds__(kThreads, 1) combine_bwd_fused_kernel(topo_com
         const int drow = (warp & 3) * 16 + (lane & 15);
         float* dst = g == 0 ? G.g_att_w1 : (g - 1 < n_msgs ? G.g_wprod[g - 1] : nullptr);
         if (dst != nullptr) {
+            const bool vec_ok = (reinterpret_cast<uintptr_t>(dst) & 15) == 0;
             const uint32_t src = (g == 0 ? tm_dw1 : tm_dwp + (g - 1) * 64) + lane_addr;
 #pragma unroll 1
             for (int c8 = 0; c8 < 8; ++c8) {
                 float v[8];
                 tmem_ld8(src + c8 * 8, v);
                 if (lane < 16) {
+                    float* d8 = dst + drow * kC + c8 * 8;
+                    if (vec_ok) {                          // 16-byte aligned accumulators: two 4-wide reductions
+                        red_add_v4(d8, v[0], v[1], v[2], v[3]);
+                        red_add_v4(d8 + 4, v[4], v[5], v[6], v[7]);
+                    } else {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) atomicAdd(dst + drow * kC + c8 * 8 + i, v[i]);
+                        for (int i = 0; i < 8; ++i) atomicAdd(d8 + i, v[i]);
+                    }
                 }
             }
         }
