@@ -25,9 +25,9 @@ params = _make_params(ch, n_msgs, aggs, ws, scales, x, tensors, 1e-5, True, save
 out = torch.zeros(rows, ch, device="cuda")
 flush = torch.empty(64 * 1024 * 1024, device="cuda")
 names = {0: "full kernel", 1: "no saved_m/pre stores", 2: "no GELU", 4: "no image stores", 8: "no prefetch loads", 16: "no MMA",
-         32: "no tile-end reads/stores", 64: "no TMEM loads", 1 | 32: "no stores at all", 1 | 8 | 32: "no global traffic",
-         1 | 2 | 4 | 8 | 16 | 32 | 64: "skeleton only", 2 | 4 | 16 | 64: "memory only", 127 | 128: "skeleton, no tile end",
-         127 | 256: "skeleton, no x loads", 127 | 128 | 256: "skeleton, neither", 128: "full, no tile end"}
+         32: "no tile-end reads/stores", 64: "no TMEM loads", 256: "no residual loads", 1 | 32: "no stores at all",
+         8 | 256: "no loads at all", 1 | 8 | 32 | 256: "no global traffic",
+         2 | 4 | 16 | 64: "memory only", 1 | 2 | 4 | 8 | 16 | 32 | 64 | 256: "skeleton only"}
 for mask, name in names.items():
     raw.topo_debug_fwd16_mask(mask)
     ts = []

@@ -66,6 +66,7 @@ struct Group {
     int ro[4];            // compact row offset of this sample per rank
     int lane;             // lane within the group
     unsigned mask;        // the whole warp takes part in every shuffle
+    unsigned dense;       // bit r: all simplices of rank r are active in this sample (the index lookups are identities)
     bool valid;           // this group owns a live row
 
     __device__ __forceinline__ F4 load(const float* base, int row) const {
@@ -104,6 +105,7 @@ struct Group {
         return v;
     }
     __device__ __forceinline__ int row_of(const DeviceTables& d, int r, int id) const {
+        if (dense & (1u << r)) return ro[r] + id;       // every simplex of the rank is active: position == id
         const int p = pos[d.off[r] + id];
         return p < 0 ? -1 : ro[r] + p;
     }
@@ -155,7 +157,9 @@ __device__ __forceinline__ void gather4(const Group<L>& g, const float* base, co
 
 // Decode blockIdx.x -> (rank, sample, local row) for this group.  Groups past the live rows stay in the
 // kernel (the shuffles are warp-wide) with valid == false and id == 0.
-template <int L>
+// kDense: test whether whole ranks are active and skip the position / id lookups for them (forward kernels; the
+// backward kernels run at 32 registers and have none to spare for the flag).
+template <int L, bool kDense>
 __device__ __forceinline__ void locate(const DeviceTables& d, const Sections& sec, const topo_complex_view& cv,
                                        Group<L>* g, int* rank, int* row, int* id, long long* axis) {
     constexpr int kGroups = kThreads / L;
@@ -166,21 +170,30 @@ __device__ __forceinline__ void locate(const DeviceTables& d, const Sections& se
     const int chunks = r == 0 ? sec.chunks[0] : (r == 1 ? sec.chunks[1] : (r == 2 ? sec.chunks[2] : sec.chunks[3]));
     const int off_r = r == 0 ? d.off[0] : (r == 1 ? d.off[1] : (r == 2 ? d.off[2] : d.off[3]));
     const int rel = blk - begin;
-    const int b = rel / chunks;
+    // rel / chunks without the integer-division sequence: rel < 2^24 and (rel + 0.5) / chunks is at least 0.5 / chunks
+    // away from an integer, far more than the rounding of one fp32 division
+    const int b = kDense ? __float2int_rz(__fdividef(static_cast<float>(rel) + 0.5f, static_cast<float>(chunks))) : rel / chunks;
     const int i = (rel - b * chunks) * kGroups + threadIdx.x / L;
     const long long ax = static_cast<long long>(b) * d.off[4];
     g->probs = cv.probs + ax;
     g->pos = cv.pos + ax;
     g->lane = threadIdx.x % L;
     g->mask = 0xffffffffu;
-    g->valid = i < cv.counts[b * 4 + r];
+    g->dense = 0u;
+    if constexpr (kDense) {
+        const int4 cnt = __ldg(reinterpret_cast<const int4*>(cv.counts) + b);
+        g->dense = (cnt.x == d.cnt[0] ? 1u : 0u) | (cnt.y == d.cnt[1] ? 2u : 0u) | (cnt.z == d.cnt[2] ? 4u : 0u) | (cnt.w == d.cnt[3] ? 8u : 0u);
+        g->valid = i < (r == 0 ? cnt.x : (r == 1 ? cnt.y : (r == 2 ? cnt.z : cnt.w)));
+    } else {
+        g->valid = i < cv.counts[b * 4 + r];
+    }
     const int B1 = static_cast<int>(cv.batch) + 1;
 #pragma unroll
     for (int q = 0; q < 4; ++q) g->ro[q] = cv.row_off[q * B1 + b];
     const int ro_r = r == 0 ? g->ro[0] : (r == 1 ? g->ro[1] : (r == 2 ? g->ro[2] : g->ro[3]));
     *rank = r;
     *row = ro_r + (g->valid ? i : 0);
-    *id = g->valid ? cv.act_idx[ax + off_r + i] : 0;
+    *id = g->valid ? ((g->dense & (1u << r)) ? i : cv.act_idx[ax + off_r + i]) : 0;
     *axis = ax;
 }
 
@@ -225,7 +238,7 @@ __global__ void __launch_bounds__(kThreads) agg_cross_fwd(const DeviceTables d, 
     Group<L> g;
     int r, row, id;
     long long axis;
-    locate<L>(d, sec, cv, &g, &r, &row, &id, &axis);
+    locate<L, true>(d, sec, cv, &g, &r, &row, &id, &axis);
     switch (r) {
         case 0: cross_fwd_body<L, 0>(d, g, row, id, x, down, up); break;
         case 1: cross_fwd_body<L, 1>(d, g, row, id, x, down, up); break;
@@ -321,7 +334,7 @@ __global__ void __launch_bounds__(kThreads) agg_same_fwd(const DeviceTables d, c
     Group<L> g;
     int r, row, id;
     long long axis;
-    locate<L>(d, sec, cv, &g, &r, &row, &id, &axis);
+    locate<L, true>(d, sec, cv, &g, &r, &row, &id, &axis);
     switch (r) {
         case 0: same_fwd_body<L, 0>(d, g, row, id, x, down, up, same); break;
         case 1: same_fwd_body<L, 1>(d, g, row, id, x, down, up, same); break;
@@ -452,7 +465,7 @@ __global__ void __launch_bounds__(kThreads, 8) agg_same_bwd(const DeviceTables d
     Group<L> g;
     int r, row, id;
     long long axis;
-    locate<L>(d, sec, cv, &g, &r, &row, &id, &axis);
+    locate<L, false>(d, sec, cv, &g, &r, &row, &id, &axis);
     switch (r) {
         case 0: same_bwd_body<L, 0>(d, g, row, id, axis, x, down, up, g_same, g_down, g_up, g_x, g_probs); break;
         case 1: same_bwd_body<L, 1>(d, g, row, id, axis, x, down, up, g_same, g_down, g_up, g_x, g_probs); break;
@@ -521,7 +534,7 @@ __global__ void __launch_bounds__(kThreads) agg_cross_bwd(const DeviceTables d, 
     Group<L> g;
     int r, row, id;
     long long axis;
-    locate<L>(d, sec, cv, &g, &r, &row, &id, &axis);
+    locate<L, false>(d, sec, cv, &g, &r, &row, &id, &axis);
     switch (r) {
         case 0: cross_bwd_body<L, 0>(d, g, row, id, axis, x, g_down, g_up, g_x, g_probs); break;
         case 1: cross_bwd_body<L, 1>(d, g, row, id, axis, x, g_down, g_up, g_x, g_probs); break;
@@ -622,6 +635,7 @@ int check_view(const topo_tables* t, const topo_complex_view* cv, int channels) 
     TOPO_REQUIRE(t && cv, "null argument");
     TOPO_REQUIRE(t->device >= 0, "tables were built host-only");
     TOPO_REQUIRE(cv->probs && cv->pos && cv->act_idx && cv->counts && cv->row_off, "null pointer in complex view");
+    TOPO_REQUIRE((reinterpret_cast<uintptr_t>(cv->counts) & 15) == 0, "complex view: counts must be 16-byte aligned");
     TOPO_REQUIRE(cv->batch >= 0 && cv->batch <= 65535, "batch out of range");
     if (channels != 32 && channels != 64 && channels != 128) {
         set_error("channels must be 32, 64 or 128");

@@ -198,8 +198,8 @@ __global__ void __launch_bounds__(kThreads, 1) combine_fwd16_kernel(topo_combine
     tc_fence_after_sync();
     stamp(2);
     const uint32_t tmem_base = *tmem_base_smem;
-    // tensor-memory columns: [D1 | H] x 2 buffers, then H0
-    const uint32_t tm_h0 = tmem_base + 256;
+    // tensor-memory columns: three [D1 | H] accumulators, then two H0 buffers (512 in all)
+    const uint32_t tm_h0 = tmem_base + 384;
     const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
     const uint32_t slot_s[2] = {smem_u32(base + FwdSmem16::kA0), smem_u32(base + FwdSmem16::kA1)};
     uint8_t* slot_p[2] = {base + FwdSmem16::kA0, base + FwdSmem16::kA1};
@@ -211,32 +211,35 @@ __global__ void __launch_bounds__(kThreads, 1) combine_fwd16_kernel(topo_combine
 
     if (!worker) {
         // ================= MMA warp: waits for each staged unit, issues its product, commits to the slot's mbarrier =================
-        uint32_t unit_no = 0;
-        int slot = 0;
-        for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        // Units arrive in tile order (x, then the messages); message products rotate through three accumulators and the
+        // x products through two, so that a unit can be issued while the epilogues of the previous tile still read theirs.
+        uint32_t unit_no = 0, acc = 0, tile_no = 0;
+        for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++tile_no) {
 #pragma unroll 1
             for (int u = 0; u < n_units; ++u, ++unit_no) {
-                named_bar_sync(1 + (unit_no & 1u), kThreads);       // all 512 workers have staged unit u (and are past epilogue u - 2)
+                const int slot = n_slots == 2 ? static_cast<int>(unit_no & 1u) : 0;
+                named_bar_sync(1 + (unit_no & 1u), kThreads);       // all 512 workers have staged this unit
                 if (lane == 0) {
                     tc_fence_after_sync();
                     const int k = u - (has_x ? 1 : 0);
                     if (dbg & 16) {
                     } else if (k < 0) {
-                        gemm_bf16x3_unrolled<kC / 16>(tm_h0, k_major(slot_s[slot], kTileRows), k_major(w1_s, kC), idesc_bf16(128, 64, 0, 0), 0);
+                        gemm_bf16x3_unrolled<kC / 16>(tm_h0 + (tile_no & 1u) * 64, k_major(slot_s[slot], kTileRows), k_major(w1_s, kC),
+                                                      idesc_bf16(128, 64, 0, 0), 0);
                     } else {
-                        gemm_bf16x3_unrolled<kC / 16>(tmem_base + (k & 1) * 128, k_major(slot_s[slot], kTileRows),
+                        gemm_bf16x3_unrolled<kC / 16>(tmem_base + acc * 128, k_major(slot_s[slot], kTileRows),
                                                       mn_major(wv_s + k * 2 * kWImg, kC, kWImg), idesc_bf16(128, 128, 0, 1), 0);
                     }
                     mma_commit(&bars[slot]);
                 }
                 __syncwarp();
-                slot = n_slots == 2 ? slot ^ 1 : 0;
+                if (u >= (has_x ? 1 : 0)) acc = acc == 2 ? 0 : acc + 1;
             }
         }
     } else {
     // ================= workers =================
     uint32_t par0 = 0u, par1 = 0u;
-    int pend0 = -1, pend1 = -1;     // unit whose MMAs are in flight on operand slot 0 / 1 (-1: none)
+    int pend0 = -1, pend1 = -1;     // number of the unit whose MMAs are in flight on operand slot 0 / 1 (-1: none)
     // wait until the MMAs that last read operand slot s (and wrote their accumulator) are complete
     auto drain = [&](int s) {
         if (s == 0) {
@@ -251,21 +254,57 @@ __global__ void __launch_bounds__(kThreads, 1) combine_fwd16_kernel(topo_combine
         return k < 0 ? P.x : (k == 0 ? P.agg[0] : (k == 1 ? P.agg[1] : P.agg[2]));
     };
 
-    float pf[2][8];                 // the next unit's rows, chunk map
-    {
-        const long long row0 = static_cast<long long>(blockIdx.x) * kTileRows;
+    // ---- the staging stream: units in tile order, numbered from 0, running AHEAD of the epilogues across tile borders ----
+    float pf[2][8];                 // rows of the next unit to stage (chunk map), loaded when the previous one was staged
+    long long s_tile = blockIdx.x;  // tile / unit of the next unit to stage
+    int s_u = 0;
+    int staged = 0;                 // units staged so far = number of the next one
+    auto load_pf = [&]() {
+        const long long nrow0 = s_tile * kTileRows;
+        const float* __restrict__ src = unit_src(s_u);
 #pragma unroll
-        for (int j = 0; j < 2; ++j) load_chunk(unit_src(0), row0 + ra + 64 * j, c, row0 + ra + 64 * j < live, pf[j]);
+        for (int j = 0; j < 2; ++j)
+            load_chunk(src, nrow0 + ra + 64 * j, c, !(dbg & 8) && s_tile < tiles && (nrow0 + ra + 64 * j < live), pf[j]);
+    };
+    auto stage_next = [&]() {
+        if (s_tile >= tiles) return;
+        const int slot = n_slots == 2 ? (staged & 1) : 0;
+        drain(slot);
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+            if (!(dbg & 4)) store_split8(slot_p[slot], kPart, ra + 64 * j, c, pf[j]);
+        fence_async_shared();
+        tc_fence_before_sync();
+        named_bar_arrive(1 + (staged & 1), kThreads);      // hand over to the MMA warp: arrive, do not wait
+        if (slot == 0) pend0 = staged; else pend1 = staged;
+        ++staged;
+        if (++s_u == n_units) { s_u = 0; s_tile += gridDim.x; }
+        load_pf();
+    };
+    load_pf();
+    stage_next();
+    if (has_x) stage_next();
+
+    const int hx = has_x ? 1 : 0;
+    uint32_t acc0 = 0;              // accumulator of this tile's first message
+    uint32_t tile_no = 0;
+    float xr[kCW];                  // row map: this thread's slice of the residual row
+    {
+        const long long row = static_cast<long long>(blockIdx.x) * kTileRows + r;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (has_x && row < live && !(dbg & 256)) t = ldg_pinned(reinterpret_cast<const float4*>(P.x + row * kC + col0) + j);
+            xr[4 * j] = t.x; xr[4 * j + 1] = t.y; xr[4 * j + 2] = t.z; xr[4 * j + 3] = t.w;
+        }
     }
-    int slot = 0;                   // slot of the unit being staged (runs on across tiles)
-    uint32_t unit_no = 0;
-    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++tile_no) {
         const long long row0 = tile * kTileRows;
         const long long row = row0 + r;
         const bool row_alive = row < live;
-        // every line this CTA reads for its next tile goes to L2 now, a whole tile ahead of the register loads
+        // every line this CTA reads two tiles from now goes to L2 (the register loads run up to a tile ahead)
         {
-            const long long prow0 = (tile + gridDim.x) * kTileRows;
+            const long long prow0 = (tile + 2 * static_cast<long long>(gridDim.x)) * kTileRows;
             if ((c & 3) == 0 && !(dbg & 8)) {
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
@@ -276,101 +315,73 @@ __global__ void __launch_bounds__(kThreads, 1) combine_fwd16_kernel(topo_combine
                 }
             }
         }
-        float xr[kCW];              // row map: this thread's slice of the residual row (in L2 since the previous tile)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (has_x && row_alive && !(dbg & 256)) t = ldg_pinned(reinterpret_cast<const float4*>(P.x + row * kC + col0) + j);
-            xr[4 * j] = t.x; xr[4 * j + 1] = t.y; xr[4 * j + 2] = t.z; xr[4 * j + 3] = t.w;
-        }
-        int prev_slot = 0;
+        const uint32_t tm_h0_t = tm_h0 + (tile_no & 1u) * 64 + lane_addr + col0;
+        const int id0 = static_cast<int>(tile_no) * n_units + hx;       // unit number of this tile's first message
 #pragma unroll 1
-        for (int u = 0; u <= n_units; ++u) {
-            if (u < n_units) {
-                // ---- stage unit u and hand it to the MMA warp (arrive, do not wait) ----
-                drain(slot);
-#pragma unroll
-                for (int j = 0; j < 2; ++j)
-                    if (!(dbg & 4)) store_split8(slot_p[slot], kPart, ra + 64 * j, c, pf[j]);
-                fence_async_shared();
-                tc_fence_before_sync();
-                named_bar_arrive(1 + (unit_no & 1u), kThreads);
-                ++unit_no;
-                if (slot == 0) pend0 = u; else pend1 = u;
-                // prefetch the next unit (of this tile, or the first one of this CTA's next tile)
+        for (int k = 0; k < n_msgs; ++k) {
+            stage_next();           // keeps the stream one unit ahead of this epilogue (two with a residual)
+            // ---- epilogue of message k ----
+            {
+                const int id = id0 + k;
+                const int es = n_slots == 2 ? (id & 1) : 0;
+                if ((es == 0 ? pend0 : pend1) == id) drain(es);
+                uint32_t ak = acc0 + k;
+                if (ak >= 3) ak -= 3;
+                const uint32_t tm = tmem_base + ak * 128 + lane_addr + col0;
+                const float sk = k == 0 ? scale_r[0] : (k == 1 ? scale_r[1] : scale_r[2]);
+                // the message first, so that its registers are free again before the GELU evaluations need theirs
                 {
-                    const bool wrap = u + 1 == n_units;
-                    const long long nrow0 = wrap ? (tile + gridDim.x) * kTileRows : row0;
-                    const float* __restrict__ src = unit_src(wrap ? 0 : u + 1);
-                    const bool any = !wrap || (tile + gridDim.x < tiles);
-#pragma unroll
-                    for (int j = 0; j < 2; ++j) load_chunk(src, nrow0 + ra + 64 * j, c, !(dbg & 8) && any && (nrow0 + ra + 64 * j < live), pf[j]);
-                }
-            }
-            // ---- epilogue of unit u - 1 ----
-            if (u >= 1) {
-                const int k = u - 1 - (has_x ? 1 : 0);
-                if ((prev_slot == 0 ? pend0 : pend1) == u - 1) drain(prev_slot);   // (one slot: already drained before staging)
-                if (k >= 0) {
-                    const uint32_t tm = tmem_base + (k & 1) * 128 + lane_addr + col0;
-                    const float sk = k == 0 ? scale_r[0] : (k == 1 ? scale_r[1] : scale_r[2]);
-                    // the message first, so that its registers are free again before the GELU evaluations need theirs
-                    {
-                        float m[kCW];
-                        if (!(dbg & 64)) {
-                            tmem_ld16(tm, m);
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < kCW; ++i) m[i] = 0.01f * i;
-                        }
-#pragma unroll
-                        for (int i = 0; i < kCW; ++i) m[i] = fmaf(sk, m[i], xr[i]);
-                        float4* pm = reinterpret_cast<float4*>(P.saved_m[k]) + tf_index(row0, q, r);
-                        if (row_alive && !(dbg & 1)) {
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) pm[j * kTileRows] = make_float4(m[4 * j], m[4 * j + 1], m[4 * j + 2], m[4 * j + 3]);
-                        }
-                    }
-                    float h[kCW];
+                    float m[kCW];
                     if (!(dbg & 64)) {
-                        tmem_ld16(tm + 64, h);
+                        tmem_ld16(tm, m);
                     } else {
 #pragma unroll
-                        for (int i = 0; i < kCW; ++i) h[i] = 0.01f * i;
-                    }
-                    if (has_x && !(dbg & 64)) {
-                        float h0[kCW];
-                        tmem_ld16(tm_h0 + lane_addr + col0, h0);
-#pragma unroll
-                        for (int i = 0; i < kCW; ++i) h[i] += h0[i];
+                        for (int i = 0; i < kCW; ++i) m[i] = 0.01f * i;
                     }
 #pragma unroll
-                    for (int i = 0; i < kCW; ++i) h[i] += vecs[col0 + i];          // pre-GELU hidden activation
-                    float4* pp = reinterpret_cast<float4*>(P.saved_pre[k]) + tf_index(row0, q, r);
+                    for (int i = 0; i < kCW; ++i) m[i] = fmaf(sk, m[i], xr[i]);
+                    float4* pm = reinterpret_cast<float4*>(P.saved_m[k]) + tf_index(row0, q, r);
                     if (row_alive && !(dbg & 1)) {
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) pp[j * kTileRows] = make_float4(h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]);
+                        for (int j = 0; j < 4; ++j) pm[j * kTileRows] = make_float4(m[4 * j], m[4 * j + 1], m[4 * j + 2], m[4 * j + 3]);
                     }
-                    float part = 0.f;
-#pragma unroll
-                    for (int i = 0; i < kCW; i += 4) {
-                        float cdf[4], pdf[4];
-                        gelu_cdf_pdf_n<4>(h + i, cdf, pdf);
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) part = fmaf((dbg & 2) ? h[i + e] : h[i + e] * cdf[e], vecs[kC + col0 + i + e], part);
-                    }
-                    red[(k * 4 + q) * kTileRows + r] = part;
                 }
+                float h[kCW];
+                if (!(dbg & 64)) {
+                    tmem_ld16(tm + 64, h);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < kCW; ++i) h[i] = 0.01f * i;
+                }
+                if (has_x && !(dbg & 64)) {
+                    float h0[kCW];
+                    tmem_ld16(tm_h0_t, h0);
+#pragma unroll
+                    for (int i = 0; i < kCW; ++i) h[i] += h0[i];
+                }
+#pragma unroll
+                for (int i = 0; i < kCW; ++i) h[i] += vecs[col0 + i];          // pre-GELU hidden activation
+                float4* pp = reinterpret_cast<float4*>(P.saved_pre[k]) + tf_index(row0, q, r);
+                if (row_alive && !(dbg & 1)) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) pp[j * kTileRows] = make_float4(h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]);
+                }
+                float part = 0.f;
+#pragma unroll
+                for (int i = 0; i < kCW; i += 4) {
+                    float cdf[4], pdf[4];
+                    gelu_cdf_pdf_n<4>(h + i, cdf, pdf);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) part = fmaf((dbg & 2) ? h[i + e] : h[i + e] * cdf[e], vecs[kC + col0 + i + e], part);
+                }
+                red[(k * 4 + q) * kTileRows + r] = part;
                 tc_fence_before_sync();
             }
-            if (u < n_units) {
-                prev_slot = slot;
-                slot = n_slots == 2 ? slot ^ 1 : 0;
-            }
         }
+        // with a residual the stream is two units ahead: the next tile's first message is issued underneath the tile end
+        if (has_x) stage_next();
         // ---------------- tile end: softmax over the messages, mix, LayerNorm ----------------
         if (tile == blockIdx.x) stamp(3);
-        if (dbg & 128) continue;
         named_bar_sync(3, kWorkers);                       // the partial scores are in `red`
         float att[3];
         {
@@ -395,10 +406,12 @@ __global__ void __launch_bounds__(kThreads, 1) combine_fwd16_kernel(topo_combine
         for (int k = 0; k < 3; ++k) {
             if (k < n_msgs) {
                 if (k + 2 >= n_msgs) {
-                    // the last two messages' products are still in tensor memory (buffer k & 1 is only overwritten by
-                    // message k + 2): m_k = s_k D1_k + x again, without a trip to L2
+                    // the last two messages' products are still in tensor memory (an accumulator is only overwritten by
+                    // the third message after it): m_k = s_k D1_k + x again, without a trip to L2
                     float d1[kCW];
-                    tmem_ld16(tmem_base + (k & 1) * 128 + lane_addr + col0, d1);
+                    uint32_t ak = acc0 + k;
+                    if (ak >= 3) ak -= 3;
+                    tmem_ld16(tmem_base + ak * 128 + lane_addr + col0, d1);
                     const float sk = k == 0 ? scale_r[0] : (k == 1 ? scale_r[1] : scale_r[2]);
 #pragma unroll
                     for (int i = 0; i < kCW; ++i) y[i] = fmaf(att[k], fmaf(sk, d1[i], xr[i]), y[i]);
@@ -417,6 +430,16 @@ __global__ void __launch_bounds__(kThreads, 1) combine_fwd16_kernel(topo_combine
             }
         }
         tc_fence_before_sync();
+        // the residual slice of this CTA's next tile (in L2 since two tiles ago) travels underneath the LayerNorm
+        {
+            const long long nrow = (tile + gridDim.x) * kTileRows + r;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (has_x && nrow < live && !(dbg & 256)) t = ldg_pinned(reinterpret_cast<const float4*>(P.x + nrow * kC + col0) + j);
+                xr[4 * j] = t.x; xr[4 * j + 1] = t.y; xr[4 * j + 2] = t.z; xr[4 * j + 3] = t.w;
+            }
+        }
         if (P.apply_ln) {
             // Row statistics with ONE exchange: every thread reduces its 16 columns to (sum, squared deviations from
             // its own mean) and the four partials of a row are merged exactly (Chan et al.): no E[y^2] - mean^2.
@@ -429,12 +452,6 @@ __global__ void __launch_bounds__(kThreads, 1) combine_fwd16_kernel(topo_combine
             for (int i = 0; i < kCW; ++i) dev = fmaf(y[i] - lmean, y[i] - lmean, dev);
             red[(3 * 4 + q) * kTileRows + r] = part;
             red[(4 * 4 + q) * kTileRows + r] = dev;
-            float4 gm[4], bt[4];                           // gamma / beta: 64 floats, L1 resident
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                gm[j] = __ldg(reinterpret_cast<const float4*>(P.ln_gamma + col0) + j);
-                bt[j] = __ldg(reinterpret_cast<const float4*>(P.ln_beta + col0) + j);
-            }
             named_bar_sync(3, kWorkers);
             const float* rs = red + 3 * 4 * kTileRows;
             const float* rd = red + 4 * 4 * kTileRows;
@@ -445,14 +462,15 @@ __global__ void __launch_bounds__(kThreads, 1) combine_fwd16_kernel(topo_combine
                              static_cast<float>(kCW) * ((d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3));
             const float rstd = 1.0f / sqrtf(m2 * (1.0f / kC) + P.ln_eps);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                y[4 * j] = fmaf((y[4 * j] - mean) * rstd, gm[j].x, bt[j].x);
-                y[4 * j + 1] = fmaf((y[4 * j + 1] - mean) * rstd, gm[j].y, bt[j].y);
-                y[4 * j + 2] = fmaf((y[4 * j + 2] - mean) * rstd, gm[j].z, bt[j].z);
-                y[4 * j + 3] = fmaf((y[4 * j + 3] - mean) * rstd, gm[j].w, bt[j].w);
+            for (int j = 0; j < 4; ++j) {                  // gamma / beta: 64 floats, L1 resident
+                const float4 gm = __ldg(reinterpret_cast<const float4*>(P.ln_gamma + col0) + j);
+                const float4 bt = __ldg(reinterpret_cast<const float4*>(P.ln_beta + col0) + j);
+                y[4 * j] = fmaf((y[4 * j] - mean) * rstd, gm.x, bt.x);
+                y[4 * j + 1] = fmaf((y[4 * j + 1] - mean) * rstd, gm.y, bt.y);
+                y[4 * j + 2] = fmaf((y[4 * j + 2] - mean) * rstd, gm.z, bt.z);
+                y[4 * j + 3] = fmaf((y[4 * j + 3] - mean) * rstd, gm.w, bt.w);
             }
-        }
-        else {
+        } else {
             named_bar_sync(3, kWorkers);                   // without the exchange: the score slots must be read by everyone
         }
         if (row_alive && !(dbg & 32)) {
@@ -462,6 +480,8 @@ __global__ void __launch_bounds__(kThreads, 1) combine_fwd16_kernel(topo_combine
         }
         // no barrier here: the score slots are not read after the exchange above, and the statistics slots are next
         // written behind the next tile's score barrier, which no thread passes before it has read them
+        acc0 += static_cast<uint32_t>(n_msgs);
+        while (acc0 >= 3) acc0 -= 3;
         if (tile == blockIdx.x) stamp(4);
     }
     }   // workers
