@@ -73,8 +73,8 @@ __device__ __forceinline__ void load_chunk(const float* __restrict__ src, long l
     float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
     if (ok) {
         const float4* p = reinterpret_cast<const float4*>(src + row * kC) + chunk * 2;
-        a = ldg_pinned(p);            // issued where written: these are prefetches into registers
-        b = ldg_pinned(p + 1);
+        a = ldg_pinned_once(p);       // issued where written: these are prefetches into registers; every row-major
+        b = ldg_pinned_once(p + 1);   // input of this kernel (dout, agg_k, row-major saved tensors) is read exactly once
     }
     v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
 }
@@ -89,8 +89,8 @@ __device__ __forceinline__ void load_saved(const float* __restrict__ src, bool t
     float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
     if (ok) {
         const float4* p = reinterpret_cast<const float4*>(src) + tf_index_chunk(row0, tile_row, chunk);
-        a = ldg_pinned(p);
-        b = ldg_pinned(p + kTileRows);
+        a = ldg_pinned_once(p);
+        b = ldg_pinned_once(p + kTileRows);
     }
     v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
 }

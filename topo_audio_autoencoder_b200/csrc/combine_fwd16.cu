@@ -66,12 +66,17 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-__device__ __forceinline__ void load_chunk(const float* __restrict__ src, long long row, int chunk, bool ok, float (&v)[8]) {
+__device__ __forceinline__ void load_chunk(const float* __restrict__ src, long long row, int chunk, bool ok, bool once, float (&v)[8]) {
     float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
     if (ok) {
         const float4* p = reinterpret_cast<const float4*>(src + row * kC) + chunk * 2;
-        a = ldg_pinned(p);
-        b = ldg_pinned(p + 1);
+        if (once) {                   // the aggregates are read once here (and once in the backward, far later)
+            a = ldg_pinned_once(p);
+            b = ldg_pinned_once(p + 1);
+        } else {                      // x is read again by the row map
+            a = ldg_pinned(p);
+            b = ldg_pinned(p + 1);
+        }
     }
     v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
 }
@@ -255,6 +260,7 @@ __global__ void __launch_bounds__(kThreads, 1) combine_fwd16_kernel(topo_combine
     };
 
     // ---- the staging stream: units in tile order, numbered from 0, running AHEAD of the epilogues across tile borders ----
+    const int hx = has_x ? 1 : 0;
     float pf[2][8];                 // rows of the next unit to stage (chunk map), loaded when the previous one was staged
     long long s_tile = blockIdx.x;  // tile / unit of the next unit to stage
     int s_u = 0;
@@ -264,7 +270,7 @@ __global__ void __launch_bounds__(kThreads, 1) combine_fwd16_kernel(topo_combine
         const float* __restrict__ src = unit_src(s_u);
 #pragma unroll
         for (int j = 0; j < 2; ++j)
-            load_chunk(src, nrow0 + ra + 64 * j, c, !(dbg & 8) && s_tile < tiles && (nrow0 + ra + 64 * j < live), pf[j]);
+            load_chunk(src, nrow0 + ra + 64 * j, c, !(dbg & 8) && s_tile < tiles && (nrow0 + ra + 64 * j < live), s_u >= hx, pf[j]);
     };
     auto stage_next = [&]() {
         if (s_tile >= tiles) return;
@@ -285,7 +291,6 @@ __global__ void __launch_bounds__(kThreads, 1) combine_fwd16_kernel(topo_combine
     stage_next();
     if (has_x) stage_next();
 
-    const int hx = has_x ? 1 : 0;
     uint32_t acc0 = 0;              // accumulator of this tile's first message
     uint32_t tile_no = 0;
     float xr[kCW];                  // row map: this thread's slice of the residual row
@@ -343,7 +348,7 @@ __global__ void __launch_bounds__(kThreads, 1) combine_fwd16_kernel(topo_combine
                     float4* pm = reinterpret_cast<float4*>(P.saved_m[k]) + tf_index(row0, q, r);
                     if (row_alive && !(dbg & 1)) {
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) pm[j * kTileRows] = make_float4(m[4 * j], m[4 * j + 1], m[4 * j + 2], m[4 * j + 3]);
+                        for (int j = 0; j < 4; ++j) __stcs(pm + j * kTileRows, make_float4(m[4 * j], m[4 * j + 1], m[4 * j + 2], m[4 * j + 3]));
                     }
                 }
                 float h[kCW];
@@ -364,7 +369,7 @@ __global__ void __launch_bounds__(kThreads, 1) combine_fwd16_kernel(topo_combine
                 float4* pp = reinterpret_cast<float4*>(P.saved_pre[k]) + tf_index(row0, q, r);
                 if (row_alive && !(dbg & 1)) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) pp[j * kTileRows] = make_float4(h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]);
+                    for (int j = 0; j < 4; ++j) __stcs(pp + j * kTileRows, make_float4(h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]));
                 }
                 float part = 0.f;
 #pragma unroll

@@ -74,6 +74,14 @@ __device__ __forceinline__ float4 ldg_pinned(const float4* p) {
     return v;
 }
 
+// the same for data that is read exactly once (saved activations in the backward): evict-first in L1 and L2, so that
+// the streams that ARE re-read soon (gradients handed to the next kernel) keep their L2 lines
+__device__ __forceinline__ float4 ldg_pinned_once(const float4* p) {
+    float4 v;
+    asm volatile("ld.global.cs.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
+
 // ---- proxy / tcgen05 fences ------------------------------------------------------------------
 // generic-proxy shared-memory writes -> visible to the async proxy (tcgen05.mma operand reads)
 __device__ __forceinline__ void fence_async_shared() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
