@@ -70,13 +70,7 @@ struct Group {
     bool valid;           // this group owns a live row
 
     __device__ __forceinline__ F4 load(const float* base, int row) const {
-        // gathered rows are read again by other groups: keep them in L2 ahead of the streams that pass through once
-        unsigned long long keep;
-        asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(keep));
-        float4 t;
-        asm("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
-            : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w)
-            : "l"(reinterpret_cast<const float4*>(base) + static_cast<long long>(row) * L + lane), "l"(keep));
+        const float4 t = __ldg(reinterpret_cast<const float4*>(base) + static_cast<long long>(row) * L + lane);
         F4 r;
         r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w;
         return r;
