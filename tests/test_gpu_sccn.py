@@ -91,6 +91,18 @@ def _complex_inputs(n, batch, regime, seed):
     N = sum(tab.sizes)
     if regime == "full":
         probs = torch.rand(batch, N, generator=g) * 0.98 + 0.01
+    elif regime == "mixed":
+        # fully active and partly active ranks side by side (the aggregation skips the index lookups per sample and
+        # rank when the whole rank is active): sample 0 everything, sample 1 loses triangles (and with them their
+        # tetrahedra), sample 2 only tetrahedra
+        probs = torch.rand(batch, N, generator=g) * 0.98 + 0.01
+        off = [0, tab.sizes[0], tab.sizes[0] + tab.sizes[1], tab.sizes[0] + tab.sizes[1] + tab.sizes[2]]
+        if batch > 1:
+            kill = torch.rand(tab.sizes[2], generator=g) < 0.3
+            probs[1, off[2]:off[3]][kill] = 0.0
+        if batch > 2:
+            kill = torch.rand(tab.sizes[3], generator=g) < 0.4
+            probs[2, off[3]:][kill] = 0.0
     else:
         probs = hard_concrete_like((batch, N), g, p_zero=0.12, p_one=0.15)
     return tab, probs
@@ -118,7 +130,7 @@ def _oracle_stage(ref, tab, probs, emb_params, weights):
 
 
 @pytest.mark.parametrize("n,batch,regime,layers,channels", [
-    (8, 3, "hc", 1, 64), (8, 2, "full", 2, 64), (20, 2, "hc", 6, 64), (20, 1, "full", 6, 64), (9, 2, "hc", 2, 32)])
+    (8, 3, "hc", 1, 64), (8, 2, "full", 2, 64), (8, 3, "mixed", 2, 64), (20, 2, "hc", 6, 64), (20, 1, "full", 6, 64), (9, 2, "hc", 2, 32)])
 def test_matrix_free_stage_matches_oracle(n, batch, regime, layers, channels):
     import topo_audio_autoencoder_b200 as T
     tab, probs = _complex_inputs(n, batch, regime, seed=n * 31 + batch)
