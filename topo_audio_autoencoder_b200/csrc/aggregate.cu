@@ -39,28 +39,35 @@ struct Sections {
     int chunks[4];  // row chunks per sample for each rank
 };
 
-struct F4 {
-    float v[4];
-    __device__ __forceinline__ void zero() { v[0] = v[1] = v[2] = v[3] = 0.f; }
-    __device__ __forceinline__ void fma(float w, const F4& x) {
+// V float4s per lane: lane l of a row's group holds float4 number l, l + L, ... of the row (every 128-bit access of
+// the group is one contiguous run of 16 L bytes)
+template <int V>
+struct FV {
+    float v[4 * V];
+    __device__ __forceinline__ void zero() {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) v[k] = fmaf(w, x.v[k], v[k]);
+        for (int k = 0; k < 4 * V; ++k) v[k] = 0.f;
     }
-    __device__ __forceinline__ void add(const F4& x) {
+    __device__ __forceinline__ void fma(float w, const FV& x) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) v[k] += x.v[k];
+        for (int k = 0; k < 4 * V; ++k) v[k] = fmaf(w, x.v[k], v[k]);
     }
-    __device__ __forceinline__ float dot(const F4& x) const {
+    __device__ __forceinline__ void add(const FV& x) {
+#pragma unroll
+        for (int k = 0; k < 4 * V; ++k) v[k] += x.v[k];
+    }
+    __device__ __forceinline__ float dot(const FV& x) const {
         float s = 0.f;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) s = fmaf(v[k], x.v[k], s);
+        for (int k = 0; k < 4 * V; ++k) s = fmaf(v[k], x.v[k], s);
         return s;
     }
 };
 
-// One group's view of its row.  L = lanes per row = C / 4.
-template <int L>
+// One group's view of its row.  L = lanes per row, V = float4s per lane: C = 4 L V.
+template <int L, int V>
 struct Group {
+    using F4 = FV<V>;
     const float* probs;   // this sample's simplex axis
     const int* pos;
     int ro[4];            // compact row offset of this sample per rank
@@ -70,9 +77,13 @@ struct Group {
     bool valid;           // this group owns a live row
 
     __device__ __forceinline__ F4 load(const float* base, int row) const {
-        const float4 t = __ldg(reinterpret_cast<const float4*>(base) + static_cast<long long>(row) * L + lane);
+        const float4* p = reinterpret_cast<const float4*>(base) + static_cast<long long>(row) * (L * V) + lane;
         F4 r;
-        r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w;
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            const float4 t = __ldg(p + j * L);
+            r.v[4 * j] = t.x; r.v[4 * j + 1] = t.y; r.v[4 * j + 2] = t.z; r.v[4 * j + 3] = t.w;
+        }
         return r;
     }
     __device__ __forceinline__ F4 load_if(bool ok, const float* base, int row) const {
@@ -82,21 +93,31 @@ struct Group {
         return r;
     }
     __device__ __forceinline__ F4 load_rw(const float* base, int row) const {   // not through the read-only path
-        const float4 t = *(reinterpret_cast<const float4*>(base) + static_cast<long long>(row) * L + lane);
+        const float4* p = reinterpret_cast<const float4*>(base) + static_cast<long long>(row) * (L * V) + lane;
         F4 r;
-        r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w;
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            const float4 t = p[j * L];
+            r.v[4 * j] = t.x; r.v[4 * j + 1] = t.y; r.v[4 * j + 2] = t.z; r.v[4 * j + 3] = t.w;
+        }
         return r;
     }
     __device__ __forceinline__ void store(float* base, int row, const F4& x) const {
-        if (valid)
-            *(reinterpret_cast<float4*>(base) + static_cast<long long>(row) * L + lane) = make_float4(x.v[0], x.v[1], x.v[2], x.v[3]);
+        if (valid) {
+            float4* p = reinterpret_cast<float4*>(base) + static_cast<long long>(row) * (L * V) + lane;
+#pragma unroll
+            for (int j = 0; j < V; ++j) p[j * L] = make_float4(x.v[4 * j], x.v[4 * j + 1], x.v[4 * j + 2], x.v[4 * j + 3]);
+        }
     }
     __device__ __forceinline__ void accumulate(float* base, int row, const F4& x) const {
         if (valid) {
-            float4* p = reinterpret_cast<float4*>(base) + static_cast<long long>(row) * L + lane;
-            float4 t = *p;
-            t.x += x.v[0]; t.y += x.v[1]; t.z += x.v[2]; t.w += x.v[3];
-            *p = t;
+            float4* p = reinterpret_cast<float4*>(base) + static_cast<long long>(row) * (L * V) + lane;
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+                float4 t = p[j * L];
+                t.x += x.v[4 * j]; t.y += x.v[4 * j + 1]; t.z += x.v[4 * j + 2]; t.w += x.v[4 * j + 3];
+                p[j * L] = t;
+            }
         }
     }
     __device__ __forceinline__ float group_sum(float v) const {
@@ -113,8 +134,8 @@ struct Group {
 
 // f(ok, row, p_s) for every coface slot of simplex `id` (rank R), four slots at a time; ok == false
 // marks an inactive coface or a padding slot (its load is predicated off).
-template <int L, int R, typename F>
-__device__ __forceinline__ void for_cofaces(const DeviceTables& d, const Group<L>& g, int id, F&& f) {
+template <int L, int V, int R, typename F>
+__device__ __forceinline__ void for_cofaces(const DeviceTables& d, const Group<L, V>& g, int id, F&& f) {
     const int w = d.ncof[R];
     const int* cof = d.cofaces[R] + static_cast<long long>(id) * w;
     for (int jb = 0; jb < w; jb += L) {
@@ -142,15 +163,15 @@ __device__ __forceinline__ void for_cofaces(const DeviceTables& d, const Group<L
 }
 
 // rows of the (R+1) faces of simplex `id` (rank R >= 1); -1 for an inactive face
-template <int L, int R>
-__device__ __forceinline__ void face_rows(const DeviceTables& d, const Group<L>& g, int id, int (&rows)[R + 1]) {
+template <int L, int V, int R>
+__device__ __forceinline__ void face_rows(const DeviceTables& d, const Group<L, V>& g, int id, int (&rows)[R + 1]) {
     const int* fc = d.faces[R] + static_cast<long long>(id) * (R + 1);
 #pragma unroll
     for (int a = 0; a <= R; ++a) rows[a] = g.row_of(d, R - 1, __ldg(fc + a));
 }
 
-template <int L>
-__device__ __forceinline__ void gather4(const Group<L>& g, const float* base, const int (&rr)[4], F4 (&v)[4]) {
+template <int L, int V>
+__device__ __forceinline__ void gather4(const Group<L, V>& g, const float* base, const int (&rr)[4], FV<V> (&v)[4]) {
 #pragma unroll
     for (int q = 0; q < 4; ++q) v[q] = g.load_if(rr[q] >= 0, base, rr[q]);
 }
@@ -159,9 +180,9 @@ __device__ __forceinline__ void gather4(const Group<L>& g, const float* base, co
 // kernel (the shuffles are warp-wide) with valid == false and id == 0.
 // kDense: test whether whole ranks are active and skip the position / id lookups for them (forward kernels; the
 // backward kernels run at 32 registers and have none to spare for the flag).
-template <int L, bool kDense>
+template <int L, int V, bool kDense>
 __device__ __forceinline__ void locate(const DeviceTables& d, const Sections& sec, const topo_complex_view& cv,
-                                       Group<L>* g, int* rank, int* row, int* id, long long* axis) {
+                                       Group<L, V>* g, int* rank, int* row, int* id, long long* axis) {
     constexpr int kGroups = kThreads / L;
     const int blk = blockIdx.x;
     const int r = (blk >= sec.begin[1]) + (blk >= sec.begin[2]) + (blk >= sec.begin[3]);
@@ -198,16 +219,16 @@ __device__ __forceinline__ void locate(const DeviceTables& d, const Sections& se
 }
 
 // ------------------------------------------------------------------ forward, phase 1: cross-rank
-template <int L, int R>
-__device__ __forceinline__ void cross_fwd_body(const DeviceTables& d, const Group<L>& g, int row, int id, const Feat& x,
+template <int L, int V, int R>
+__device__ __forceinline__ void cross_fwd_body(const DeviceTables& d, const Group<L, V>& g, int row, int id, const Feat& x,
                                                const FeatMut& down, const FeatMut& up) {
     if constexpr (R < 3) {             // down[R] = sum over cofaces p_s X_{R+1}[s]
         if (d.cnt[R + 1] > 0) {
-            F4 acc;
+            FV<V> acc;
             acc.zero();
-            for_cofaces<L, R>(d, g, id, [&](const int (&rr)[4], const float (&pp)[4]) {
-                F4 v[4];
-                gather4(g, x.p[R + 1], rr, v);
+            for_cofaces<L, V, R>(d, g, id, [&](const int (&rr)[4], const float (&pp)[4]) {
+                FV<V> v[4];
+                gather4<L, V>(g, x.p[R + 1], rr, v);
 #pragma unroll
                 for (int q = 0; q < 4; ++q) acc.fma(pp[q], v[q]);
             });
@@ -216,41 +237,41 @@ __device__ __forceinline__ void cross_fwd_body(const DeviceTables& d, const Grou
     }
     if constexpr (R > 0) {             // up[R] = p_id * sum over active faces X_{R-1}[f]
         int fr[R + 1];
-        face_rows<L, R>(d, g, id, fr);
-        F4 acc;
+        face_rows<L, V, R>(d, g, id, fr);
+        FV<V> acc;
         acc.zero();
-        F4 v[R + 1];
+        FV<V> v[R + 1];
 #pragma unroll
         for (int a = 0; a <= R; ++a) v[a] = g.load_if(fr[a] >= 0, x.p[R - 1], fr[a]);
 #pragma unroll
         for (int a = 0; a <= R; ++a) acc.add(v[a]);
         const float p = g.probs[d.off[R] + id];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) acc.v[k] *= p;
+        for (int k = 0; k < 4 * V; ++k) acc.v[k] *= p;
         g.store(up.p[R], row, acc);
     }
 }
 
-template <int L>
+template <int L, int V>
 __global__ void __launch_bounds__(kThreads) agg_cross_fwd(const DeviceTables d, const Sections sec,
                                                           const topo_complex_view cv, const Feat x, const FeatMut down,
                                                           const FeatMut up) {
-    Group<L> g;
+    Group<L, V> g;
     int r, row, id;
     long long axis;
-    locate<L, true>(d, sec, cv, &g, &r, &row, &id, &axis);
+    locate<L, V, true>(d, sec, cv, &g, &r, &row, &id, &axis);
     switch (r) {
-        case 0: cross_fwd_body<L, 0>(d, g, row, id, x, down, up); break;
-        case 1: cross_fwd_body<L, 1>(d, g, row, id, x, down, up); break;
-        case 2: cross_fwd_body<L, 2>(d, g, row, id, x, down, up); break;
-        default: cross_fwd_body<L, 3>(d, g, row, id, x, down, up); break;
+        case 0: cross_fwd_body<L, V, 0>(d, g, row, id, x, down, up); break;
+        case 1: cross_fwd_body<L, V, 1>(d, g, row, id, x, down, up); break;
+        case 2: cross_fwd_body<L, V, 2>(d, g, row, id, x, down, up); break;
+        default: cross_fwd_body<L, V, 3>(d, g, row, id, x, down, up); break;
     }
 }
 
 // ------------------------------------------------------------------ forward, phase 2: same-rank
 // A0[v,v'] = p_e: walk the vertex's edges, gather the other endpoint.  f(rows[4], p_e[4]).
-template <int L, typename F>
-__device__ __forceinline__ void for_vertex_neighbours(const DeviceTables& d, const Group<L>& g, int id, F&& f) {
+template <int L, int V, typename F>
+__device__ __forceinline__ void for_vertex_neighbours(const DeviceTables& d, const Group<L, V>& g, int id, F&& f) {
     const int w = d.ncof[0];
     const int* cof = d.cofaces[0] + static_cast<long long>(id) * w;
     for (int jb = 0; jb < w; jb += L) {
@@ -278,15 +299,15 @@ __device__ __forceinline__ void for_vertex_neighbours(const DeviceTables& d, con
     }
 }
 
-template <int L, int R>
-__device__ __forceinline__ void same_fwd_body(const DeviceTables& d, const Group<L>& g, int row, int id, const Feat& x,
+template <int L, int V, int R>
+__device__ __forceinline__ void same_fwd_body(const DeviceTables& d, const Group<L, V>& g, int row, int id, const Feat& x,
                                               const Feat& down, const Feat& up, const FeatMut& same) {
-    F4 acc;
+    FV<V> acc;
     acc.zero();
     if constexpr (R == 0) {
-        for_vertex_neighbours<L>(d, g, id, [&](const int (&rr)[4], const float (&pp)[4]) {
-            F4 v[4];
-            gather4(g, x.p[0], rr, v);
+        for_vertex_neighbours<L, V>(d, g, id, [&](const int (&rr)[4], const float (&pp)[4]) {
+            FV<V> v[4];
+            gather4<L, V>(g, x.p[0], rr, v);
 #pragma unroll
             for (int q = 0; q < 4; ++q) acc.fma(pp[q], v[q]);
         });
@@ -294,24 +315,24 @@ __device__ __forceinline__ void same_fwd_body(const DeviceTables& d, const Group
         // same[R] = sum_{s > id} p_s up[R+1][s]  -  (sum p_s^2) X_R[id]
         float qsum = 0.f;
         if (d.cnt[R + 1] > 0)
-            for_cofaces<L, R>(d, g, id, [&](const int (&rr)[4], const float (&pp)[4]) {
-                F4 v[4];
-                gather4(g, up.p[R + 1], rr, v);
+            for_cofaces<L, V, R>(d, g, id, [&](const int (&rr)[4], const float (&pp)[4]) {
+                FV<V> v[4];
+                gather4<L, V>(g, up.p[R + 1], rr, v);
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     acc.fma(pp[q], v[q]);
                     if (rr[q] >= 0) qsum = fmaf(pp[q], pp[q], qsum);
                 }
             });
-        const F4 own = g.load_if(g.valid, x.p[R], row);
+        const FV<V> own = g.load_if(g.valid, x.p[R], row);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) acc.v[k] = fmaf(-qsum, own.v[k], acc.v[k]);
+        for (int k = 0; k < 4 * V; ++k) acc.v[k] = fmaf(-qsum, own.v[k], acc.v[k]);
     } else {
         // same[3] = p (sum_{t < id, active} down[2][t] - c p X_3[id])
         int fr[4];
-        face_rows<L, 3>(d, g, id, fr);
-        F4 v[4];
-        gather4(g, down.p[2], fr, v);
+        face_rows<L, V, 3>(d, g, id, fr);
+        FV<V> v[4];
+        gather4<L, V>(g, down.p[2], fr, v);
         int n_faces = 0;
 #pragma unroll
         for (int a = 0; a < 4; ++a) {
@@ -319,48 +340,48 @@ __device__ __forceinline__ void same_fwd_body(const DeviceTables& d, const Group
             n_faces += fr[a] >= 0;
         }
         const float p = g.probs[d.off[3] + id];
-        const F4 own = g.load_if(g.valid, x.p[3], row);
+        const FV<V> own = g.load_if(g.valid, x.p[3], row);
         const float cp = static_cast<float>(n_faces) * p;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) acc.v[k] = p * fmaf(-cp, own.v[k], acc.v[k]);
+        for (int k = 0; k < 4 * V; ++k) acc.v[k] = p * fmaf(-cp, own.v[k], acc.v[k]);
     }
     g.store(same.p[R], row, acc);
 }
 
-template <int L>
+template <int L, int V>
 __global__ void __launch_bounds__(kThreads) agg_same_fwd(const DeviceTables d, const Sections sec,
                                                          const topo_complex_view cv, const Feat x, const Feat down,
                                                          const Feat up, const FeatMut same) {
-    Group<L> g;
+    Group<L, V> g;
     int r, row, id;
     long long axis;
-    locate<L, true>(d, sec, cv, &g, &r, &row, &id, &axis);
+    locate<L, V, true>(d, sec, cv, &g, &r, &row, &id, &axis);
     switch (r) {
-        case 0: same_fwd_body<L, 0>(d, g, row, id, x, down, up, same); break;
-        case 1: same_fwd_body<L, 1>(d, g, row, id, x, down, up, same); break;
-        case 2: same_fwd_body<L, 2>(d, g, row, id, x, down, up, same); break;
-        default: same_fwd_body<L, 3>(d, g, row, id, x, down, up, same); break;
+        case 0: same_fwd_body<L, V, 0>(d, g, row, id, x, down, up, same); break;
+        case 1: same_fwd_body<L, V, 1>(d, g, row, id, x, down, up, same); break;
+        case 2: same_fwd_body<L, V, 2>(d, g, row, id, x, down, up, same); break;
+        default: same_fwd_body<L, V, 3>(d, g, row, id, x, down, up, same); break;
     }
 }
 
 // ------------------------------------------------------------------ backward, stage X: same-rank
 // Updates g_up[2], g_up[3], g_down[2] in place (owner rows only), adds the diagonal and A0 terms to
 // g_x, and the direct probability derivatives to g_probs.
-template <int L, int R>
-__device__ __forceinline__ void same_bwd_body(const DeviceTables& d, const Group<L>& g, int row, int id, long long axis,
+template <int L, int V, int R>
+__device__ __forceinline__ void same_bwd_body(const DeviceTables& d, const Group<L, V>& g, int row, int id, long long axis,
                                               const Feat& x, const Feat& down, const Feat& up, const Feat& g_same,
                                               const FeatMut& g_down, const FeatMut& g_up, const FeatMut& g_x,
                                               float* __restrict__ g_probs) {
     const float p = g.probs[d.off[R] + id];
     float gp = 0.f;            // d loss / d p_id collected by this group (lane-partial dot products)
-    F4 gx;                     // addition to g_x[R][row]
+    FV<V> gx;                     // addition to g_x[R][row]
     gx.zero();
 
     if constexpr (R == 0) {
         // same[0] = A0 X0, A0 symmetric:  g_x0[v] += sum_{v'} p_e g_same0[v']
-        for_vertex_neighbours<L>(d, g, id, [&](const int (&rr)[4], const float (&pp)[4]) {
-            F4 v[4];
-            gather4(g, g_same.p[0], rr, v);
+        for_vertex_neighbours<L, V>(d, g, id, [&](const int (&rr)[4], const float (&pp)[4]) {
+            FV<V> v[4];
+            gather4<L, V>(g, g_same.p[0], rr, v);
 #pragma unroll
             for (int q = 0; q < 4; ++q) gx.fma(pp[q], v[q]);
         });
@@ -368,24 +389,24 @@ __device__ __forceinline__ void same_bwd_body(const DeviceTables& d, const Group
     if constexpr (R == 1) {
         // owner of p_e for A0: d/dp_e = <g_same0[v], X0[v']> + <g_same0[v'], X0[v]>
         int fr[2];
-        face_rows<L, 1>(d, g, id, fr);
+        face_rows<L, V, 1>(d, g, id, fr);
         const bool both = fr[0] >= 0 && fr[1] >= 0;
-        const F4 ga = g.load_if(both, g_same.p[0], fr[0]), gb = g.load_if(both, g_same.p[0], fr[1]);
-        const F4 xa = g.load_if(both, x.p[0], fr[0]), xb = g.load_if(both, x.p[0], fr[1]);
+        const FV<V> ga = g.load_if(both, g_same.p[0], fr[0]), gb = g.load_if(both, g_same.p[0], fr[1]);
+        const FV<V> xa = g.load_if(both, x.p[0], fr[0]), xb = g.load_if(both, x.p[0], fr[1]);
         gp += ga.dot(xb) + gb.dot(xa);
     }
     if constexpr (R == 1 || R == 2) {
         // diagonal of same[R]: g_x[R] -= q g_same[R],  q = sum_{s > id} p_s^2
         if (d.cnt[R + 1] > 0) {
             float qsum = 0.f;
-            for_cofaces<L, R>(d, g, id, [&](const int (&rr)[4], const float (&pp)[4]) {
+            for_cofaces<L, V, R>(d, g, id, [&](const int (&rr)[4], const float (&pp)[4]) {
 #pragma unroll
                 for (int q = 0; q < 4; ++q)
                     if (rr[q] >= 0) qsum = fmaf(pp[q], pp[q], qsum);
             });
-            const F4 gs = g.load_if(g.valid, g_same.p[R], row);
+            const FV<V> gs = g.load_if(g.valid, g_same.p[R], row);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) gx.v[k] = fmaf(-qsum, gs.v[k], gx.v[k]);
+            for (int k = 0; k < 4 * V; ++k) gx.v[k] = fmaf(-qsum, gs.v[k], gx.v[k]);
         }
     }
     if constexpr (R == 2 || R == 3) {
@@ -393,14 +414,14 @@ __device__ __forceinline__ void same_bwd_body(const DeviceTables& d, const Group
         //   Rsum = sum_{f < id} g_same[R-1][f];  g_up[R][id] += p Rsum;
         //   d/dp = <Rsum, up[R][id]> - 2 p sum_f <g_same[R-1][f], X_{R-1}[f]>
         int fr[R + 1];
-        face_rows<L, R>(d, g, id, fr);
-        F4 gf[R + 1], xf[R + 1];
+        face_rows<L, V, R>(d, g, id, fr);
+        FV<V> gf[R + 1], xf[R + 1];
 #pragma unroll
         for (int a = 0; a <= R; ++a) {
             gf[a] = g.load_if(fr[a] >= 0, g_same.p[R - 1], fr[a]);
             xf[a] = g.load_if(fr[a] >= 0, x.p[R - 1], fr[a]);
         }
-        F4 rsum;
+        FV<V> rsum;
         rsum.zero();
         float diag = 0.f;
 #pragma unroll
@@ -408,20 +429,20 @@ __device__ __forceinline__ void same_bwd_body(const DeviceTables& d, const Group
             rsum.add(gf[a]);
             diag += gf[a].dot(xf[a]);
         }
-        const F4 u = g.load_if(g.valid, up.p[R], row);
+        const FV<V> u = g.load_if(g.valid, up.p[R], row);
         gp += rsum.dot(u) - 2.0f * p * diag;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) rsum.v[k] *= p;
+        for (int k = 0; k < 4 * V; ++k) rsum.v[k] *= p;
         g.accumulate(g_up.p[R], row, rsum);
     }
     if constexpr (R == 2) {
         if (d.cnt[3] > 0) {
             // same[3] = I_3^T down[2] - ...:  g_down[2][t] += sum_{s > t} p_s g_same[3][s]
-            F4 acc;
+            FV<V> acc;
             acc.zero();
-            for_cofaces<L, 2>(d, g, id, [&](const int (&rr)[4], const float (&pp)[4]) {
-                F4 v[4];
-                gather4(g, g_same.p[3], rr, v);
+            for_cofaces<L, V, 2>(d, g, id, [&](const int (&rr)[4], const float (&pp)[4]) {
+                FV<V> v[4];
+                gather4<L, V>(g, g_same.p[3], rr, v);
 #pragma unroll
                 for (int q = 0; q < 4; ++q) acc.fma(pp[q], v[q]);
             });
@@ -431,10 +452,10 @@ __device__ __forceinline__ void same_bwd_body(const DeviceTables& d, const Group
     if constexpr (R == 3) {
         // direct p dependence of same[3] = p sum_t down[2][t] - c p^2 X3, and its diagonal
         int fr[4];
-        face_rows<L, 3>(d, g, id, fr);
-        F4 v[4];
-        gather4(g, down.p[2], fr, v);
-        F4 sum_d;
+        face_rows<L, V, 3>(d, g, id, fr);
+        FV<V> v[4];
+        gather4<L, V>(g, down.p[2], fr, v);
+        FV<V> sum_d;
         sum_d.zero();
         int n_faces = 0;
 #pragma unroll
@@ -442,12 +463,12 @@ __device__ __forceinline__ void same_bwd_body(const DeviceTables& d, const Group
             sum_d.add(v[a]);
             n_faces += fr[a] >= 0;
         }
-        const F4 gs = g.load_if(g.valid, g_same.p[3], row);
-        const F4 own = g.load_if(g.valid, x.p[3], row);
+        const FV<V> gs = g.load_if(g.valid, g_same.p[3], row);
+        const FV<V> own = g.load_if(g.valid, x.p[3], row);
         const float cf = static_cast<float>(n_faces);
         gp += gs.dot(sum_d) - 2.0f * cf * p * gs.dot(own);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) gx.v[k] = fmaf(-cf * p * p, gs.v[k], gx.v[k]);
+        for (int k = 0; k < 4 * V; ++k) gx.v[k] = fmaf(-cf * p * p, gs.v[k], gx.v[k]);
     }
 
     g.accumulate(g_x.p[R], row, gx);
@@ -457,30 +478,30 @@ __device__ __forceinline__ void same_bwd_body(const DeviceTables& d, const Group
     }
 }
 
-template <int L>
-__global__ void __launch_bounds__(kThreads, 8) agg_same_bwd(const DeviceTables d, const Sections sec,
+template <int L, int V>
+__global__ void __launch_bounds__(kThreads, V == 1 ? 8 : 5) agg_same_bwd(const DeviceTables d, const Sections sec,
                                                          const topo_complex_view cv, const Feat x, const Feat down,
                                                          const Feat up, const Feat g_same, const FeatMut g_down,
                                                          const FeatMut g_up, const FeatMut g_x, float* __restrict__ g_probs) {
-    Group<L> g;
+    Group<L, V> g;
     int r, row, id;
     long long axis;
-    locate<L, false>(d, sec, cv, &g, &r, &row, &id, &axis);
+    locate<L, V, false>(d, sec, cv, &g, &r, &row, &id, &axis);
     switch (r) {
-        case 0: same_bwd_body<L, 0>(d, g, row, id, axis, x, down, up, g_same, g_down, g_up, g_x, g_probs); break;
-        case 1: same_bwd_body<L, 1>(d, g, row, id, axis, x, down, up, g_same, g_down, g_up, g_x, g_probs); break;
-        case 2: same_bwd_body<L, 2>(d, g, row, id, axis, x, down, up, g_same, g_down, g_up, g_x, g_probs); break;
-        default: same_bwd_body<L, 3>(d, g, row, id, axis, x, down, up, g_same, g_down, g_up, g_x, g_probs); break;
+        case 0: same_bwd_body<L, V, 0>(d, g, row, id, axis, x, down, up, g_same, g_down, g_up, g_x, g_probs); break;
+        case 1: same_bwd_body<L, V, 1>(d, g, row, id, axis, x, down, up, g_same, g_down, g_up, g_x, g_probs); break;
+        case 2: same_bwd_body<L, V, 2>(d, g, row, id, axis, x, down, up, g_same, g_down, g_up, g_x, g_probs); break;
+        default: same_bwd_body<L, V, 3>(d, g, row, id, axis, x, down, up, g_same, g_down, g_up, g_x, g_probs); break;
     }
 }
 
 // ------------------------------------------------------------------ backward, stage Y: cross-rank
 // With the TOTAL g_down / g_up:  down[R-1] = I_R X_R,  up[R] = I_R^T X_{R-1}.
-template <int L, int R>
-__device__ __forceinline__ void cross_bwd_body(const DeviceTables& d, const Group<L>& g, int row, int id, long long axis,
+template <int L, int V, int R>
+__device__ __forceinline__ void cross_bwd_body(const DeviceTables& d, const Group<L, V>& g, int row, int id, long long axis,
                                                const Feat& x, const Feat& g_down, const Feat& g_up, const FeatMut& g_x,
                                                float* __restrict__ g_probs) {
-    F4 gx;
+    FV<V> gx;
     gx.zero();
     float gp = 0.f;
     if constexpr (R >= 1) {
@@ -488,14 +509,14 @@ __device__ __forceinline__ void cross_bwd_body(const DeviceTables& d, const Grou
         // as the coface s of down[R-1]:  Rsum = sum_f g_down[R-1][f];  g_x += p Rsum;  d/dp = <Rsum, X_R[s]>
         // as the target of up[R]:        d/dp = <g_up[R][s], sum_f X_{R-1}[f]>
         int fr[R + 1];
-        face_rows<L, R>(d, g, id, fr);
-        F4 gf[R + 1], xf[R + 1];
+        face_rows<L, V, R>(d, g, id, fr);
+        FV<V> gf[R + 1], xf[R + 1];
 #pragma unroll
         for (int a = 0; a <= R; ++a) {
             gf[a] = g.load_if(fr[a] >= 0, g_down.p[R - 1], fr[a]);
             xf[a] = g.load_if(fr[a] >= 0, x.p[R - 1], fr[a]);
         }
-        F4 rsum, qsum;
+        FV<V> rsum, qsum;
         rsum.zero();
         qsum.zero();
 #pragma unroll
@@ -503,18 +524,18 @@ __device__ __forceinline__ void cross_bwd_body(const DeviceTables& d, const Grou
             rsum.add(gf[a]);
             qsum.add(xf[a]);
         }
-        const F4 own = g.load_if(g.valid, x.p[R], row);
-        const F4 gu = g.load_if(g.valid, g_up.p[R], row);
+        const FV<V> own = g.load_if(g.valid, x.p[R], row);
+        const FV<V> gu = g.load_if(g.valid, g_up.p[R], row);
         gp = rsum.dot(own) + qsum.dot(gu);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) gx.v[k] = p * rsum.v[k];
+        for (int k = 0; k < 4 * V; ++k) gx.v[k] = p * rsum.v[k];
     }
     if constexpr (R < 3) {
         if (d.cnt[R + 1] > 0) {
             // as a face of up[R+1]:  g_x[R][f] += sum_{s > f} p_s g_up[R+1][s]
-            for_cofaces<L, R>(d, g, id, [&](const int (&rr)[4], const float (&pp)[4]) {
-                F4 v[4];
-                gather4(g, g_up.p[R + 1], rr, v);
+            for_cofaces<L, V, R>(d, g, id, [&](const int (&rr)[4], const float (&pp)[4]) {
+                FV<V> v[4];
+                gather4<L, V>(g, g_up.p[R + 1], rr, v);
 #pragma unroll
                 for (int q = 0; q < 4; ++q) gx.fma(pp[q], v[q]);
             });
@@ -527,19 +548,19 @@ __device__ __forceinline__ void cross_bwd_body(const DeviceTables& d, const Grou
     }
 }
 
-template <int L>
+template <int L, int V>
 __global__ void __launch_bounds__(kThreads) agg_cross_bwd(const DeviceTables d, const Sections sec,
                                                           const topo_complex_view cv, const Feat x, const Feat g_down,
                                                           const Feat g_up, const FeatMut g_x, float* __restrict__ g_probs) {
-    Group<L> g;
+    Group<L, V> g;
     int r, row, id;
     long long axis;
-    locate<L, false>(d, sec, cv, &g, &r, &row, &id, &axis);
+    locate<L, V, false>(d, sec, cv, &g, &r, &row, &id, &axis);
     switch (r) {
-        case 0: cross_bwd_body<L, 0>(d, g, row, id, axis, x, g_down, g_up, g_x, g_probs); break;
-        case 1: cross_bwd_body<L, 1>(d, g, row, id, axis, x, g_down, g_up, g_x, g_probs); break;
-        case 2: cross_bwd_body<L, 2>(d, g, row, id, axis, x, g_down, g_up, g_x, g_probs); break;
-        default: cross_bwd_body<L, 3>(d, g, row, id, axis, x, g_down, g_up, g_x, g_probs); break;
+        case 0: cross_bwd_body<L, V, 0>(d, g, row, id, axis, x, g_down, g_up, g_x, g_probs); break;
+        case 1: cross_bwd_body<L, V, 1>(d, g, row, id, axis, x, g_down, g_up, g_x, g_probs); break;
+        case 2: cross_bwd_body<L, V, 2>(d, g, row, id, axis, x, g_down, g_up, g_x, g_probs); break;
+        default: cross_bwd_body<L, V, 3>(d, g, row, id, axis, x, g_down, g_up, g_x, g_probs); break;
     }
 }
 
@@ -649,12 +670,15 @@ int check_view(const topo_tables* t, const topo_complex_view* cv, int channels) 
 
 using namespace topo;
 
-#define DISPATCH_LANES(channels, CALL)                  \
-    switch (channels) {                                 \
-        case 32: { constexpr int L = 8; CALL; } break;  \
-        case 64: { constexpr int L = 16; CALL; } break; \
-        default: { constexpr int L = 32; CALL; } break; \
+// lanes per row and float4s per lane: C = 64 runs with 8 lanes x 2 float4s (four rows per warp: the index arithmetic of
+// a row is paid once per warp instruction, so twice as many rows share it)
+#define DISPATCH_LANES(channels, CALL)                                  \
+    switch (channels) {                                                 \
+        case 32: { constexpr int L = 8, V = 1; CALL; } break;           \
+        case 64: { constexpr int L = 8, V = 2; CALL; } break;           \
+        default: { constexpr int L = 32, V = 1; CALL; } break;          \
     }
+static int lanes_per_row(int channels) { return channels == 32 ? 8 : (channels == 64 ? 8 : 32); }
 
 #define DISPATCH_VEC(channels, CALL)                      \
     switch (channels) {                                   \
@@ -681,11 +705,11 @@ extern "C" int topo_sccn_aggregate_fwd(const topo_tables* t, const topo_complex_
             TOPO_REQUIRE(r == 3 || d.cnt[r + 1] == 0 || down[r], "missing down buffer");
         }
     }
-    const Sections sec = make_sections(d, cv->batch, kThreads / (channels / 4));
+    const Sections sec = make_sections(d, cv->batch, kThreads / lanes_per_row(channels));
     if (sec.begin[4] == 0) return TOPO_OK;
     cudaStream_t s = as_stream(stream);
-    DISPATCH_LANES(channels, (agg_cross_fwd<L><<<sec.begin[4], kThreads, 0, s>>>(d, sec, *cv, fx, mdown, mup)));
-    DISPATCH_LANES(channels, (agg_same_fwd<L><<<sec.begin[4], kThreads, 0, s>>>(d, sec, *cv, fx, fdown, fup, msame)));
+    DISPATCH_LANES(channels, (agg_cross_fwd<L, V><<<sec.begin[4], kThreads, 0, s>>>(d, sec, *cv, fx, mdown, mup)));
+    DISPATCH_LANES(channels, (agg_same_fwd<L, V><<<sec.begin[4], kThreads, 0, s>>>(d, sec, *cv, fx, fdown, fup, msame)));
     TOPO_LAUNCH_CHECK();
     return TOPO_OK;
 }
@@ -707,12 +731,12 @@ extern "C" int topo_sccn_aggregate_bwd(const topo_tables* t, const topo_complex_
         mgdown.p[r] = g_down[r]; mgup.p[r] = g_up[r]; mgx.p[r] = g_x[r];
         if (d.cnt[r]) TOPO_REQUIRE(x[r] && g_same[r] && g_x[r], "missing buffer for a populated rank");
     }
-    const Sections sec = make_sections(d, cv->batch, kThreads / (channels / 4));
+    const Sections sec = make_sections(d, cv->batch, kThreads / lanes_per_row(channels));
     if (sec.begin[4] == 0) return TOPO_OK;
     cudaStream_t s = as_stream(stream);
-    DISPATCH_LANES(channels, (agg_same_bwd<L><<<sec.begin[4], kThreads, 0, s>>>(
+    DISPATCH_LANES(channels, (agg_same_bwd<L, V><<<sec.begin[4], kThreads, 0, s>>>(
                                  d, sec, *cv, fx, fdown, fup, fgsame, mgdown, mgup, mgx, g_probs)));
-    DISPATCH_LANES(channels, (agg_cross_bwd<L><<<sec.begin[4], kThreads, 0, s>>>(
+    DISPATCH_LANES(channels, (agg_cross_bwd<L, V><<<sec.begin[4], kThreads, 0, s>>>(
                                  d, sec, *cv, fx, fgdown, fgup, mgx, g_probs)));
     TOPO_LAUNCH_CHECK();
     return TOPO_OK;
