@@ -240,9 +240,14 @@ def test_fused_tensor_core_backward_matches_fp64_autograd(n_msgs, apply_ln, rows
         check_one("beta", fused["beta"], two_kernel["beta"], bet.grad)
 
 
-@pytest.mark.parametrize("n_msgs,apply_ln,rows,residual", [(3, True, 1000, True), (2, False, 130, True), (1, True, 64, False),
-                                                            (2, True, 40000, True), (3, False, 5000, True), (2, True, 257, False)])
-def test_second_generation_forward_and_its_backward(n_msgs, apply_ln, rows, residual):
+@pytest.mark.parametrize("n_msgs,apply_ln,rows,residual,max_ctas", [
+    (3, True, 1000, True, 0), (2, False, 130, True, 0), (1, True, 64, False, 0), (2, True, 40000, True, 0), (3, False, 5000, True, 0),
+    (2, True, 257, False, 0),
+    # few CTAs, many tiles each: the forward's staging stream runs ahead across tile borders (three accumulators, two H0
+    # buffers) -- every message count with and without the residual unit
+    (3, True, 3000, False, 2), (1, False, 2000, False, 3), (2, True, 3000, True, 1), (1, True, 1500, True, 2), (3, True, 2500, True, 1),
+    (2, False, 2000, False, 1)])
+def test_second_generation_forward_and_its_backward(n_msgs, apply_ln, rows, residual, max_ctas):
     """topo_sccn_combine_fwd_tc2 (bf16x3, one product per message, tile-fragment saves) against fp64, with the
     FFMA forward as the accuracy yardstick; then the fused backward on its tile-fragment saves against the same
     backward on the first-generation forward's row-major saves (two layouts, one result)."""
@@ -266,7 +271,7 @@ def test_second_generation_forward_and_its_backward(n_msgs, apply_ln, rows, resi
         pad = rows_pad if gen == 2 else rows
         saved = ([torch.zeros(pad, ch, device="cuda") for _ in range(n_msgs)],
                  [torch.zeros(pad, ch, device="cuda") for _ in range(n_msgs)], torch.zeros(3, rows, device="cuda"))
-        params = _make_params(ch, n_msgs, aggs, ws, scales, x, tensors, 1e-5, apply_ln, saved, gen == 2)
+        params = _make_params(ch, n_msgs, aggs, ws, scales, x, tensors, 1e-5, apply_ln, saved, gen == 2, None, max_ctas)
         out = torch.zeros(rows, ch, device="cuda")
         fn = {0: lib.topo_sccn_combine_fwd, 1: lib.topo_sccn_combine_fwd_tc, 2: lib.topo_sccn_combine_fwd_tc2}[gen]
         check(fn(C.byref(params), rows, ptr(live, torch.int32), ptr(out), stream()))
