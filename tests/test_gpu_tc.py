@@ -359,3 +359,53 @@ def test_cta_pair_gemm_shares_the_weight_image(rows):
     report(f"tc/gemm-bf16x3/cta-pair/rows={rows}", out, want.float())
     assert torch.isfinite(out).all()
     assert err < 5e-7, f"relative-to-condition error {err:.3e}"
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n_msgs,residual,max_ctas", [(2, True, 0), (2, True, 3), (3, True, 5), (3, False, 2), (1, True, 4)])
+def test_forward_and_row_gradients_are_bit_reproducible(n_msgs, residual, max_ctas):
+    """The kernels hand shared-memory slots, operand slots and tensor-memory accumulators from one tile to the next
+    without a closing barrier; a hazard there would show up as run-to-run differences.  Ten runs of the forward (output,
+    saved activations, scores) and of the fused backward's row gradients must agree bit for bit (the parameter
+    gradients meet in global atomics across CTAs and are excluded)."""
+    import ctypes as C
+    from topo_audio_autoencoder_b200._lib import lib, check, ptr, stream, CombineGrads
+    from topo_audio_autoencoder_b200.custom_sccn import _make_params
+    rows, ch = 20000, 64
+    g = torch.Generator().manual_seed(77 + n_msgs)
+    rnd = lambda *s: torch.randn(*s, generator=g).cuda()     # noqa: E731
+    aggs = [rnd(rows, ch) * 2 for _ in range(n_msgs)]
+    ws = [rnd(ch, ch) * 0.2 for _ in range(n_msgs)]
+    scales = [torch.tensor([0.7 + 0.2 * k]).cuda() for k in range(n_msgs)]
+    x = rnd(rows, ch) if residual else None
+    tensors = [rnd(ch, ch) * 0.2, rnd(ch) * 0.1, rnd(ch) * 0.3, rnd(1), 1 + 0.1 * rnd(ch), 0.1 * rnd(ch)]
+    g_out = rnd(rows, ch)
+    pad = -(-rows // 128) * 128
+
+    def run():
+        saved = ([torch.zeros(pad, ch, device="cuda") for _ in range(n_msgs)],
+                 [torch.zeros(pad, ch, device="cuda") for _ in range(n_msgs)], torch.zeros(3, rows, device="cuda"))
+        params = _make_params(ch, n_msgs, aggs, ws, scales, x, tensors, 1e-5, True, saved, True, None, max_ctas)
+        out = torch.zeros(rows, ch, device="cuda")
+        check(lib.topo_sccn_combine_fwd_tc2(C.byref(params), rows, None, ptr(out), stream()))
+        res = {"g_agg": [torch.zeros(rows, ch, device="cuda") for _ in range(n_msgs)],
+               "wprod": [torch.zeros(ch, ch, device="cuda") for _ in range(n_msgs)],
+               "g_x": torch.zeros(rows, ch, device="cuda") if residual else None,
+               "w1": torch.zeros(ch, ch, device="cuda"), "b1": torch.zeros(ch, device="cuda"),
+               "w2": torch.zeros(ch, device="cuda"), "b2": torch.zeros(1, device="cuda"),
+               "gamma": torch.zeros(ch, device="cuda"), "beta": torch.zeros(ch, device="cuda")}
+        grads = CombineGrads()
+        for k in range(n_msgs):
+            grads.g_agg[k], grads.g_wprod[k] = ptr(res["g_agg"][k]), ptr(res["wprod"][k])
+        grads.g_x = ptr(res["g_x"])
+        grads.g_att_w1, grads.g_att_b1, grads.g_att_w2, grads.g_att_b2 = ptr(res["w1"]), ptr(res["b1"]), ptr(res["w2"]), ptr(res["b2"])
+        grads.g_ln_gamma, grads.g_ln_beta = ptr(res["gamma"]), ptr(res["beta"])
+        check(lib.topo_sccn_combine_bwd_tc(C.byref(params), rows, None, ptr(g_out), C.byref(grads), stream()))
+        torch.cuda.synchronize()
+        return [out, *saved[0], *saved[1], saved[2], *res["g_agg"]] + ([res["g_x"]] if residual else [])
+
+    first = run()
+    assert all(torch.isfinite(t).all() for t in first)
+    for it in range(9):
+        again = run()
+        for i, (a, b) in enumerate(zip(first, again)):
+            assert torch.equal(a, b), f"run {it + 1}: tensor {i} differs in {(a != b).sum().item()} elements"

@@ -1,5 +1,5 @@
 // S1 (b) forward on the tensor cores, second generation (C = 64): bf16x3 operand images (tc16.cuh), one MMA
-// round per message with NO dependent GEMM chain, operand slots and accumulators double-buffered so the
+// round per message with NO dependent GEMM chain, operand slots and accumulators multi-buffered so the
 // tensor pipe works underneath the epilogue of the previous message.
 //
 // The attention hidden layer of message k is  pre_k = W1 m_k + b1  with  m_k = s_k (agg_k W_k) + x.  Folding
@@ -7,13 +7,18 @@
 // read the SAME operand agg_k:   [ D1_k | H_k ] = agg_k [ W_k | V_k ]   is one 128 x 128 x 64 product, and
 // H0 = x W1^T is one more product per tile.  V_k (64 x 64) is formed once per CTA in fp32.
 //
-// Units of a tile: X (stages x, issues H0), then one unit per message (stages agg_k, issues [D1|H]).  The loop
-// is software-pipelined by one unit: stage u+1 and issue its MMA, then run the epilogue of unit u.
+// Units of a tile: X (stages x, issues H0), then one unit per message (stages agg_k, issues [D1|H]).  Staging is a
+// stream of its own that runs ahead of the epilogues ACROSS tile borders: before the epilogue of message k the
+// workers stage the next unit of the stream (the next message, or the next tile's X), and with a residual one more
+// before the tile end (the next tile's first message), so every operand load and every MMA has an epilogue or the tile
+// end to hide behind.  Tensor memory holds three [D1|H] accumulators (the tile end re-reads the last two messages
+// while the next tile's first one is being written) and two H0 buffers: all 512 columns.
 //   stage    (chunk map)  thread t owns columns [8c, 8c+8), c = t % 8, of tile rows t/8 and t/8 + 64: coalesced
 //                         128-bit loads, prefetched one unit ahead into registers, split into the bf16x3 image
 //   epilogue (row map)    thread (q, r) = (t / 128, t % 128) owns columns [16q, 16q+16) of row r = TMEM lane r:
 //                         m_k = s_k D1 + x,  pre_k = H + H0 + b1,  partial score  sum GELU(pre) w2
-//   tile end              scores meet in shared memory, softmax, mix, LayerNorm, store
+//   tile end              scores meet in shared memory, softmax, mix, LayerNorm (per-thread sum / squared deviations,
+//                         merged with one exchange), store
 // m_k, pre_k and the scores are SAVED for the backward in the tile-fragment layout (layout.cuh): every store and
 // every later load of these private tensors is a fully coalesced 128-bit access from the row map.
 #include <algorithm>
