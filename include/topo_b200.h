@@ -116,7 +116,7 @@ typedef struct {
     const float* probs;      /* [B, N] rectified probabilities */
     const int32_t* pos;      /* [B, N] */
     const int32_t* act_idx;  /* [B, N] */
-    const int32_t* counts;   /* [B, 4] */
+    const int32_t* counts;   /* [B, 4]; 16-byte aligned (a sample's four counts are one 128-bit load) */
     const int32_t* row_off;  /* [4, B+1] */
     int64_t batch;
 } topo_complex_view;
