@@ -182,9 +182,9 @@ __device__ __forceinline__ void gather4(const Group<L, V>& g, const float* base,
 // backward kernels run at 32 registers and have none to spare for the flag).
 template <int L, int V, bool kDense>
 __device__ __forceinline__ void locate(const DeviceTables& d, const Sections& sec, const topo_complex_view& cv,
-                                       Group<L, V>* g, int* rank, int* row, int* id, long long* axis) {
+                                       Group<L, V>* g, int* rank, int* row, int* id, long long* axis, int first_block = 0) {
     constexpr int kGroups = kThreads / L;
-    const int blk = blockIdx.x;
+    const int blk = blockIdx.x + first_block;          // a launch may cover a suffix of the sections (one rank)
     const int r = (blk >= sec.begin[1]) + (blk >= sec.begin[2]) + (blk >= sec.begin[3]);
     // selects instead of sec.begin[r]: a runtime index would copy the parameter struct to local memory
     const int begin = r == 0 ? sec.begin[0] : (r == 1 ? sec.begin[1] : (r == 2 ? sec.begin[2] : sec.begin[3]));
@@ -564,6 +564,75 @@ __global__ void __launch_bounds__(kThreads) agg_cross_bwd(const DeviceTables d, 
     }
 }
 
+// ------------------------------------------------------------------ backward, top rank: stages X and Y in one pass
+// A tetrahedron's own row is all the two stages share across rows: stage Y needs the TOTAL g_down[2] of its faces
+// (complete once stage X has run for the triangles) and the total g_up[3] of the row itself, which this kernel forms.
+// So the order  stage X (ranks 0..2)  ->  this kernel (rank 3)  ->  stage Y (ranks 0..2, which gather the total
+// g_up[3] written here)  reads x[3] once, reads and writes g_up[3] and g_x[3] once, and gathers the faces' features once.
+template <int L, int V>
+__global__ void __launch_bounds__(kThreads, 4) agg_top_bwd(const DeviceTables d, const Sections sec, const topo_complex_view cv,
+                                                           const Feat x, const Feat down, const Feat up, const Feat g_same,
+                                                           const Feat g_down, const FeatMut g_up, const FeatMut g_x,
+                                                           float* __restrict__ g_probs) {
+    Group<L, V> g;
+    int r, row, id;
+    long long axis;
+    locate<L, V, false>(d, sec, cv, &g, &r, &row, &id, &axis, sec.begin[3]);
+    using F = FV<V>;
+    const float p = g.probs[d.off[3] + id];
+    int fr[4];
+    face_rows<L, V, 3>(d, g, id, fr);
+    int n_faces = 0;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) n_faces += fr[a] >= 0;
+    const float cf = static_cast<float>(n_faces);
+
+    // stage X, as the owner of p for same[2] = I_3 up[3] - q X_2:  Rsum = sum_f g_same[2][f]
+    F rsum, qsum;                       // qsum = sum_f X_2[f] (stage Y)
+    rsum.zero();
+    qsum.zero();
+    float diag = 0.f;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        const F gf = g.load_if(fr[a] >= 0, g_same.p[2], fr[a]);
+        const F xf = g.load_if(fr[a] >= 0, x.p[2], fr[a]);
+        rsum.add(gf);
+        qsum.add(xf);
+        diag += gf.dot(xf);
+    }
+    const F u = g.load_if(g.valid, up.p[3], row);
+    float gp = rsum.dot(u) - 2.0f * p * diag;
+    F gu;                               // total g_up[3][row]
+    gu.zero();
+    if (g.valid) gu = g.load_rw(g_up.p[3], row);
+#pragma unroll
+    for (int k = 0; k < 4 * V; ++k) gu.v[k] = fmaf(p, rsum.v[k], gu.v[k]);
+    g.store(g_up.p[3], row, gu);        // stage Y of the triangles gathers it
+
+    // stage X, the direct p dependence of same[3] = p sum_t down[2][t] - c p^2 X3, and its diagonal
+    F sum_d;
+    sum_d.zero();
+#pragma unroll
+    for (int a = 0; a < 4; ++a) sum_d.add(g.load_if(fr[a] >= 0, down.p[2], fr[a]));
+    const F gs = g.load_if(g.valid, g_same.p[3], row);
+    const F own = g.load_if(g.valid, x.p[3], row);
+    gp += gs.dot(sum_d) - 2.0f * cf * p * gs.dot(own);
+
+    // stage Y, as the coface of down[2] and the target of up[3]
+    F rsum2;
+    rsum2.zero();
+#pragma unroll
+    for (int a = 0; a < 4; ++a) rsum2.add(g.load_if(fr[a] >= 0, g_down.p[2], fr[a]));
+    gp += rsum2.dot(own) + qsum.dot(gu);
+
+    F gx;
+#pragma unroll
+    for (int k = 0; k < 4 * V; ++k) gx.v[k] = fmaf(-cf * p * p, gs.v[k], p * rsum2.v[k]);
+    g.accumulate(g_x.p[3], row, gx);
+    gp = g.group_sum(gp);
+    if (g.lane == 0 && g.valid) g_probs[axis + d.off[3] + id] += gp;
+}
+
 // ------------------------------------------------------------------ generic CSR
 constexpr int kWarpsPerBlock = 8;
 
@@ -734,10 +803,18 @@ extern "C" int topo_sccn_aggregate_bwd(const topo_tables* t, const topo_complex_
     const Sections sec = make_sections(d, cv->batch, kThreads / lanes_per_row(channels));
     if (sec.begin[4] == 0) return TOPO_OK;
     cudaStream_t s = as_stream(stream);
-    DISPATCH_LANES(channels, (agg_same_bwd<L, V><<<sec.begin[4], kThreads, 0, s>>>(
-                                 d, sec, *cv, fx, fdown, fup, fgsame, mgdown, mgup, mgx, g_probs)));
-    DISPATCH_LANES(channels, (agg_cross_bwd<L, V><<<sec.begin[4], kThreads, 0, s>>>(
-                                 d, sec, *cv, fx, fgdown, fgup, mgx, g_probs)));
+    // ranks 0..2: stage X, then stage Y; the top rank runs both stages in one pass in between (agg_top_bwd)
+    const int top = d.cnt[3] > 0 ? sec.begin[4] - sec.begin[3] : 0;
+    const int low = sec.begin[4] - top;
+    if (low > 0)
+        DISPATCH_LANES(channels, (agg_same_bwd<L, V><<<low, kThreads, 0, s>>>(
+                                     d, sec, *cv, fx, fdown, fup, fgsame, mgdown, mgup, mgx, g_probs)));
+    if (top > 0)
+        DISPATCH_LANES(channels, (agg_top_bwd<L, V><<<top, kThreads, 0, s>>>(
+                                     d, sec, *cv, fx, fdown, fup, fgsame, fgdown, mgup, mgx, g_probs)));
+    if (low > 0)
+        DISPATCH_LANES(channels, (agg_cross_bwd<L, V><<<low, kThreads, 0, s>>>(
+                                     d, sec, *cv, fx, fgdown, fgup, mgx, g_probs)));
     TOPO_LAUNCH_CHECK();
     return TOPO_OK;
 }
