@@ -16,6 +16,7 @@ CMD="python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-profile-pass --
 $CMD > gpurun_out/plain.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -s 400 -c 1500 --csv --log-file gpurun_out/launches_serial.csv $CMD > gpurun_out/ncu_launches.log 2>&1
 echo "exit launches (serial): $?"
+if [ -n "$LISTS_ONLY" ]; then exit 0; fi     # LISTS_ONLY=1: the two launch lists, no --set full captures
 $CMD > gpurun_out/plain2.log 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:combine_bwd_fused -s 0 -c 4 -f -o gpurun_out/prof_bwd_final $CMD > gpurun_out/ncu_bwd.log 2>&1
 echo "exit bwd: $?"

@@ -568,10 +568,11 @@ __global__ void __launch_bounds__(kThreads) agg_cross_bwd(const DeviceTables d, 
 // A tetrahedron's own row is all the two stages share across rows: stage Y needs the TOTAL g_down[2] of its faces
 // (complete once stage X has run for the triangles) and the total g_up[3] of the row itself, which this kernel forms.
 // So the order  stage X (ranks 0..2)  ->  this kernel (rank 3)  ->  stage Y (ranks 0..2, which gather the total
-// g_up[3] written here)  reads x[3] once, reads and writes g_up[3] and g_x[3] once, and gathers the faces' features once.
+// g_up[3] written here)  reads x[3] once, reads and writes g_up[3] and g_x[3] once, gathers the faces' features once and
+// never reads up[3] (it is p times the sum of the faces' features, which are in registers anyway).
 template <int L, int V>
 __global__ void __launch_bounds__(kThreads, 4) agg_top_bwd(const DeviceTables d, const Sections sec, const topo_complex_view cv,
-                                                           const Feat x, const Feat down, const Feat up, const Feat g_same,
+                                                           const Feat x, const Feat down, const Feat g_same,
                                                            const Feat g_down, const FeatMut g_up, const FeatMut g_x,
                                                            float* __restrict__ g_probs) {
     Group<L, V> g;
@@ -600,8 +601,8 @@ __global__ void __launch_bounds__(kThreads, 4) agg_top_bwd(const DeviceTables d,
         qsum.add(xf);
         diag += gf.dot(xf);
     }
-    const F u = g.load_if(g.valid, up.p[3], row);
-    float gp = rsum.dot(u) - 2.0f * p * diag;
+    // up[3][row] = p sum_f X_2[f] is what the forward wrote (same summation order): recomputed, not re-read
+    float gp = p * rsum.dot(qsum) - 2.0f * p * diag;
     F gu;                               // total g_up[3][row]
     gu.zero();
     if (g.valid) gu = g.load_rw(g_up.p[3], row);
@@ -811,7 +812,7 @@ extern "C" int topo_sccn_aggregate_bwd(const topo_tables* t, const topo_complex_
                                      d, sec, *cv, fx, fdown, fup, fgsame, mgdown, mgup, mgx, g_probs)));
     if (top > 0)
         DISPATCH_LANES(channels, (agg_top_bwd<L, V><<<top, kThreads, 0, s>>>(
-                                     d, sec, *cv, fx, fdown, fup, fgsame, fgdown, mgup, mgx, g_probs)));
+                                     d, sec, *cv, fx, fdown, fgsame, fgdown, mgup, mgx, g_probs)));
     if (low > 0)
         DISPATCH_LANES(channels, (agg_cross_bwd<L, V><<<low, kThreads, 0, s>>>(
                                      d, sec, *cv, fx, fgdown, fgup, mgx, g_probs)));
