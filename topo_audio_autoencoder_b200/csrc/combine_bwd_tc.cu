@@ -13,11 +13,14 @@
 //       round 2:  Ga   = P  W_k^T       (P K-major,  W_k [in][out] K-major)        -> g_agg_k = scale_k Ga
 //                 DWp_k += Q^T P        (both MN-major)                             -> g_wprod[k]
 //   g_x = sum_k dm_k.  The GELU' of message k + 1 is evaluated while round 2 of message k runs.
-// DW1 and DWp_k (64 x 64 each) stay in tensor memory for the whole CTA and are added to global memory once.
-// The row-contraction MMAs are issued with M = 128: rows 64..127 of their A operand alias the next 16 KB of
-// shared memory and produce accumulator rows that are never read.
-// Column sums (b1, w2, gamma, beta gradients) are reduced over a warp's 32 rows with a halving shuffle
-// exchange (16 shuffles per 16 columns), one register per quantity per thread.
+// DW1 and DWp_k (64 x 64 each) stay in tensor memory for the whole CTA and are added to global memory once
+// (red.global.add.v4.f32).  The row-contraction MMAs are issued with M = 64 (accumulator row i in TMEM lane
+// 32 (i / 16) + i % 16), three threads share the 72 MMAs of a round.
+// Column sums (b1, w2, gamma, beta gradients) accumulate in the chunk map's registers (eight columns per thread) and
+// meet once per CTA: two shuffles per value, one pass through shared memory, one atomic per column.
+// Every global load is issued at least one phase before its first use (phase-A operands of the next tile before the
+// last MMA round is awaited, pre_{k+1} underneath round 1 of message k, pre_0 inside phase A) and everything is read
+// exactly once, with the streaming cache policy.
 #include <algorithm>
 
 #include "common.cuh"
