@@ -29,7 +29,10 @@ class StandInConv(nn.Module):
         nn.init.xavier_uniform_(self.weight, gain=1.414)
 
     def forward(self, x_source, neighborhood):
-        return torch.mm(neighborhood, torch.mm(x_source, self.weight))
+        xw = torch.mm(x_source, self.weight)
+        if neighborhood.is_sparse:          # gradient to the operator's values stays on its pattern
+            return torch.sparse.mm(neighborhood, xw)
+        return torch.mm(neighborhood, xw)
 
 
 def _present(d, key):

@@ -18,7 +18,7 @@ RTOL, ATOL = 1e-5, 1e-6
 
 
 def golden_cases():
-    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz"))
+    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz") and not f.startswith("ref_"))
 
 
 def load_golden(name):
@@ -95,3 +95,65 @@ def assert_fp32_equivalent(tag, got, ref32, ref64, factor=4.0, floor=0.0):
     # gradient of the attention output bias, zero by softmax shift invariance), given by the caller
     assert ours <= factor * theirs + 2e-7 * scale + floor, (
         f"{line}\n  vs fp64: ours {ours:.3e}, oracle fp32 {theirs:.3e}, scale {scale:.3e}")
+
+
+# ---- fixtures written by oracle/make_golden_glue.py from the reference's own encoder / SCCN / decoder code ----
+def ref_sccn_cases():
+    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.startswith("ref_sccn_") and f.endswith(".npz"))
+
+
+def load_sccn_case(fx, device="cpu"):
+    """-> (features, incidences, adjacencies, upstream) as the reference's forward takes them; absent ranks are
+    None / missing exactly as they were when the reference ran."""
+    max_rank = int(fx["max_rank"])
+    feats, ups = {}, {}
+    for r in range(max_rank + 1):
+        k = f"rank_{r}"
+        if f"present_{k}" not in fx.files:
+            continue
+        feats[k] = torch.from_numpy(fx[f"x_{k}"]).to(device) if bool(fx[f"present_{k}"]) else None
+        if feats[k] is not None:
+            ups[k] = torch.from_numpy(fx[f"up_{k}"]).to(device)
+    mats = {"adj": {}, "inc": {}}
+    for kind in mats:
+        for r in range(max_rank + 1):
+            k = f"rank_{r}"
+            if f"present_{kind}_{k}" not in fx.files:
+                continue
+            if not bool(fx[f"present_{kind}_{k}"]):
+                mats[kind][k] = None
+                continue
+            idx = torch.from_numpy(fx[f"{kind}_{k}_idx"].astype(np.int64))
+            val = torch.from_numpy(fx[f"{kind}_{k}_val"])
+            shape = tuple(int(s) for s in fx[f"{kind}_{k}_shape"])
+            mats[kind][k] = torch.sparse_coo_tensor(idx, val, shape).coalesce().to(device)
+    return feats, mats["inc"], mats["adj"], ups
+
+
+def run_sccn_case(model, feats, inc, adj, ups):
+    """forward + backward of a GradientSCCN-shaped module; -> (out, feature grads, operator-value grads by
+    ('adj'|'inc', key), parameter grads by name)."""
+    leaves = {k: v.detach().clone().requires_grad_(True) for k, v in feats.items() if v is not None}
+    f_in = {k: leaves.get(k) for k in feats}
+    inc_l = {k: (v.detach().coalesce().requires_grad_(True) if v is not None else None) for k, v in inc.items()}
+    adj_l = {k: (v.detach().coalesce().requires_grad_(True) if v is not None else None) for k, v in adj.items()}
+    out = model(f_in, inc_l, adj_l)
+    keys = [k for k in sorted(out) if out[k] is not None and out[k].requires_grad]
+    loss = sum((out[k] * ups[k]).sum() for k in keys)
+    mat_keys = [("adj", k) for k, v in adj_l.items() if v is not None] + [("inc", k) for k, v in inc_l.items() if v is not None]
+    mat_leaves = [adj_l[k] if kind == "adj" else inc_l[k] for kind, k in mat_keys]
+    named = list(model.named_parameters())
+    grads = torch.autograd.grad(loss, list(leaves.values()) + mat_leaves + [p for _, p in named], allow_unused=True)
+    nf, nm = len(leaves), len(mat_leaves)
+    gf = dict(zip(leaves.keys(), grads[:nf]))
+    gm = {}
+    for key, leaf, g in zip(mat_keys, mat_leaves, grads[nf:nf + nm]):
+        if g is None:
+            gm[key] = None
+        elif g.is_sparse:
+            gm[key] = g.coalesce().values()
+        else:                                   # dense gradient: read it on the operator's pattern
+            i = leaf.indices()
+            gm[key] = g[i[0], i[1]]
+    gp = {n: g for (n, _), g in zip(named, grads[nf + nm:])}
+    return out, gf, gm, gp
