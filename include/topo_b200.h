@@ -334,6 +334,12 @@ int topo_sccn_combine_bwd_conv_tc(const topo_combine_params* p, int64_t rows,
 int topo_sccn_combine_bwd_tc(const topo_combine_params* p, int64_t rows, const int32_t* n_rows_dev,
                              const float* grad_out, const topo_combine_grads* g, topo_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Unit-test and measurement entry points.  NOT part of the product library: libtopo_b200.so neither declares nor
+ * exports them.  They exist in libtopo_b200_debug.so, the same sources compiled with -DTOPO_DEBUG_KERNELS=1 plus
+ * csrc/gemm16_debug.cu (csrc/build.py build_debug()), which tests/test_gpu_tc.py and scripts/ablate_*.py load.
+ * ------------------------------------------------------------------------------------------- */
+#ifdef TOPO_DEBUG_KERNELS
 /* Unit-test entry of the tensor-core path (tcgen05.mma kind::tf32, 3xTF32 operand splitting):
  * out[rows, 64] = a[rows, 64] @ w[64, 64].  mode 0: both operands in shared memory (K-major SWIZZLE_128B);
  * mode 3: the A operand in tensor memory (tcgen05.st by the row threads). */
@@ -360,6 +366,7 @@ int topo_debug_gemm_bf16x3(const float* a, const float* w, int64_t rows, int mod
 void topo_debug_fwd16_mask(int mask);
 void topo_debug_fwd16_stamps(unsigned long long* device_buffer);
 void topo_debug_bwd_stamps(unsigned long long* device_buffer);
+#endif  /* TOPO_DEBUG_KERNELS */
 
 /* ---------------------------------------------------------------------------------------------
  * D1-D3. Tiled pairwise spectral distance.  Replaces the pair loop of compute_distances

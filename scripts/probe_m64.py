@@ -1,6 +1,7 @@
 """GPU: where do the 64 accumulator rows of an M = 64 tcgen05.mma land in tensor memory?"""
 import sys
 import torch
+from topo_audio_autoencoder_b200 import _lib
 sys.path.insert(0, ".")
 from topo_audio_autoencoder_b200._lib import lib, ptr, stream  # noqa: E402
 
@@ -9,7 +10,7 @@ rows = 128
 a = torch.randn(rows, 64, generator=g).cuda()
 b = torch.randn(rows, 64, generator=g).cuda()
 out = torch.zeros(128, 64, device="cuda")
-rc = lib.topo_debug_gemm_bf16x3(ptr(a), ptr(b), rows, 3, 16384, 1024, 2048, ptr(out), stream())
+rc = _lib.load_debug().topo_debug_gemm_bf16x3(ptr(a), ptr(b), rows, 3, 16384, 1024, 2048, ptr(out), stream())
 torch.cuda.synchronize()
 want = (a.double().t() @ b.double()).float()          # [64, 64]
 print("rc", rc)

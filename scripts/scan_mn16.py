@@ -3,6 +3,7 @@ import itertools
 import sys
 
 import torch
+from topo_audio_autoencoder_b200 import _lib
 
 sys.path.insert(0, ".")
 from topo_audio_autoencoder_b200._lib import lib, ptr, stream  # noqa: E402
@@ -23,7 +24,7 @@ def main():
 
     def run(mode, second, lbo, sbo, kstep, shape):
         out = torch.zeros(*shape, device="cuda")
-        rc = lib.topo_debug_gemm_bf16x3(ptr(a), ptr(second), rows, mode, lbo, sbo, kstep, ptr(out), stream())
+        rc = _lib.load_debug().topo_debug_gemm_bf16x3(ptr(a), ptr(second), rows, mode, lbo, sbo, kstep, ptr(out), stream())
         try:
             torch.cuda.synchronize()
         except Exception as e:  # noqa: BLE001

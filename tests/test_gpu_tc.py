@@ -6,6 +6,16 @@ from tests.helpers import report
 
 pytestmark = pytest.mark.gpu
 
+_DEBUG = []
+
+
+def _debug_lib():
+    """libtopo_b200_debug.so: the unit-test GEMM entry points are not part of the product library"""
+    if not _DEBUG:
+        from topo_audio_autoencoder_b200 import _lib
+        _DEBUG.append(_lib.load_debug())
+    return _DEBUG[0]
+
 
 @pytest.mark.parametrize("rows", [1, 128, 1000, 20000])
 def test_tf32x3_gemm_is_fp32_accurate(rows):
@@ -14,7 +24,7 @@ def test_tf32x3_gemm_is_fp32_accurate(rows):
     a = (torch.randn(rows, 64, generator=g) * torch.logspace(-3, 3, 64)).cuda()     # wide dynamic range per column
     w = torch.randn(64, 64, generator=g).cuda()
     out = torch.full((rows, 64), float("nan"), device="cuda")
-    check(lib.topo_debug_gemm_tf32x3(ptr(a), ptr(w), rows, 0, ptr(out), stream()))
+    check(_debug_lib().topo_debug_gemm_tf32x3(ptr(a), ptr(w), rows, 0, ptr(out), stream()))
     torch.cuda.synchronize()
     want64 = a.double() @ w.double()
     fp32 = (a @ w).double()                       # cuBLAS fp32 (no TF32) as the accuracy yardstick
@@ -73,7 +83,7 @@ def test_a_operand_from_tensor_memory():
     a = torch.randn(500, 64, generator=g).cuda()
     w = torch.randn(64, 64, generator=g).cuda()
     out = torch.full((500, 64), float("nan"), device="cuda")
-    check(lib.topo_debug_gemm_tf32x3(ptr(a), ptr(w), 500, 3, ptr(out), stream()))
+    check(_debug_lib().topo_debug_gemm_tf32x3(ptr(a), ptr(w), 500, 3, ptr(out), stream()))
     torch.cuda.synchronize()
     want = a.double() @ w.double()
     scale = a.double().abs() @ w.double().abs()
@@ -133,7 +143,7 @@ def test_bf16x3_gemm_in_both_operand_majors(mode, shape, rows):
     a = (torch.randn(rows, 64, generator=g) * torch.logspace(-3, 3, 64)).cuda()
     second = (torch.randn(rows, 64, generator=g) if mode == 2 else torch.randn(64, 64, generator=g)).cuda()
     out = torch.zeros(*(shape or (rows, 64)), device="cuda")
-    check(lib.topo_debug_gemm_bf16x3(ptr(a), ptr(second), rows, mode, 16384, 1024, 2048, ptr(out), stream()))
+    check(_debug_lib().topo_debug_gemm_bf16x3(ptr(a), ptr(second), rows, mode, 16384, 1024, 2048, ptr(out), stream()))
     torch.cuda.synchronize()
     a64, s64 = a.double(), second.double()
     if mode == 0:
@@ -351,7 +361,7 @@ def test_cta_pair_gemm_shares_the_weight_image(rows):
     a = (torch.randn(rows, 64, generator=g) * torch.logspace(-3, 3, 64)).cuda()
     w = torch.randn(64, 64, generator=g).cuda()
     out = torch.full((rows, 64), float("nan"), device="cuda")
-    check(lib.topo_debug_gemm_bf16x3(ptr(a), ptr(w), rows, 4, 0, 0, 0, ptr(out), stream()))
+    check(_debug_lib().topo_debug_gemm_bf16x3(ptr(a), ptr(w), rows, 4, 0, 0, 0, ptr(out), stream()))
     torch.cuda.synchronize()
     want = a.double() @ w.double().t()
     cond = a.double().abs() @ w.double().abs().t()

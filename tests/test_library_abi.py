@@ -12,9 +12,12 @@ from tests.helpers import ROOT
 HEADER = os.path.join(ROOT, "include", "topo_b200.h")
 
 
-def declared_functions():
+def declared_functions(debug=False):
+    """entry points the header declares for the product library, or (debug=True) only inside #ifdef TOPO_DEBUG_KERNELS"""
     text = open(HEADER).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    block = re.compile(r"#ifdef TOPO_DEBUG_KERNELS(.*?)#endif", re.S)
+    text = "\n".join(block.findall(text)) if debug else block.sub("", text)
     return sorted(set(re.findall(r"\b(topo_[a-z0-9_]+)\s*\(", text)))
 
 
@@ -31,6 +34,19 @@ def test_library_exports_every_declared_symbol():
     for name in declared_functions():
         assert hasattr(raw, name), f"{name} is declared in the header but not exported by libtopo_b200.so"
     assert raw.topo_version() >= 100
+
+
+def test_debug_entry_points_are_not_in_the_product_library():
+    from topo_audio_autoencoder_b200 import _lib
+    debug = declared_functions(debug=True)
+    assert debug == sorted(_lib.DEBUG_SIGNATURES) and all(n.startswith("topo_debug_") for n in debug)
+    assert not any(n.startswith("topo_debug_") for n in declared_functions())
+    raw = C.CDLL(_lib.LIB_PATH)
+    for name in debug:
+        assert not hasattr(raw, name), f"{name} leaked into the product library"
+    twin = C.CDLL(_lib.DEBUG_LIB_PATH)
+    for name in debug + declared_functions():
+        assert hasattr(twin, name), f"{name} missing from libtopo_b200_debug.so"
 
 
 def test_no_torch_types_cross_the_boundary():

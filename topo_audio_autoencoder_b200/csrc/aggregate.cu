@@ -725,6 +725,7 @@ Sections make_sections(const DeviceTables& d, int64_t batch, int groups_per_bloc
 int check_view(const topo_tables* t, const topo_complex_view* cv, int channels) {
     TOPO_REQUIRE(t && cv, "null argument");
     TOPO_REQUIRE(t->device >= 0, "tables were built host-only");
+    TOPO_REQUIRE_TABLES_DEVICE(t);
     TOPO_REQUIRE(cv->probs && cv->pos && cv->act_idx && cv->counts && cv->row_off, "null pointer in complex view");
     TOPO_REQUIRE((reinterpret_cast<uintptr_t>(cv->counts) & 15) == 0, "complex view: counts must be 16-byte aligned");
     TOPO_REQUIRE(cv->batch >= 0 && cv->batch <= 65535, "batch out of range");

@@ -1075,6 +1075,7 @@ extern "C" int topo_layernorm_bwd(int64_t rows, int channels, const float* x, co
 extern "C" int topo_embed_fwd(const topo_tables* t, const topo_complex_view* cv, int rank, int channels,
                               const float* lne, float* x_out, topo_stream_t stream) {
     TOPO_REQUIRE(t && cv && lne && x_out, "null argument");
+    TOPO_REQUIRE_TABLES_DEVICE(t);
     TOPO_REQUIRE(rank >= 0 && rank <= 3, "rank out of range");
     if (cv->batch == 0 || t->d.cnt[rank] == 0) return TOPO_OK;
     const dim3 grid((t->d.cnt[rank] + 7) / 8, static_cast<unsigned>(cv->batch));
@@ -1087,6 +1088,7 @@ extern "C" int topo_embed_bwd(const topo_tables* t, const topo_complex_view* cv,
                               const float* lne, const float* grad_x, float* grad_lne, float* grad_probs,
                               topo_stream_t stream) {
     TOPO_REQUIRE(t && cv && lne && grad_x && grad_lne && grad_probs, "null argument");
+    TOPO_REQUIRE_TABLES_DEVICE(t);
     TOPO_REQUIRE(rank >= 0 && rank <= 3, "rank out of range");
     if (t->d.cnt[rank] == 0) return TOPO_OK;
     cudaStream_t s = as_stream(stream);

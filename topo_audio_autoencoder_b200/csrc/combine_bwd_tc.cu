@@ -627,8 +627,10 @@ __global__ void __launch_bounds__(kThreads, 1) combine_bwd_fused_kernel(topo_com
 using namespace topo;
 
 static unsigned long long* g_bwd_stamps = nullptr;
+#if TOPO_DEBUG_KERNELS
 // globaltimer stamps of CTA 0 / thread 0 (up to 62 x uint64, see the stamp() calls) for scripts/ablate_bwd.py
 extern "C" void topo_debug_bwd_stamps(unsigned long long* device_buffer) { g_bwd_stamps = device_buffer; }
+#endif
 
 extern "C" int topo_sccn_combine_bwd_tc(const topo_combine_params* p, int64_t rows, const int32_t* n_rows_dev,
                                         const float* grad_out, const topo_combine_grads* g, topo_stream_t stream) {

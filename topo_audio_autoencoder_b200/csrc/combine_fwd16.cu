@@ -508,12 +508,14 @@ __global__ void __launch_bounds__(kThreads, 1) combine_fwd16_kernel(topo_combine
 using namespace topo;
 
 static int g_fwd16_debug_mask = 0;
+static unsigned long long* g_fwd16_stamps = nullptr;
+#if TOPO_DEBUG_KERNELS
 // Differential-timing knob for scripts/ablate_fwd16.py (0 = the real kernel; results are WRONG for any other value).
 extern "C" void topo_debug_fwd16_mask(int mask) { g_fwd16_debug_mask = mask; }
-static unsigned long long* g_fwd16_stamps = nullptr;
 // globaltimer stamps of CTA 0 / thread 0 (7 x uint64): start, set-up done, after the set-up barrier, first tile's
 // unit loop done, first tile done, all tiles done, end
 extern "C" void topo_debug_fwd16_stamps(unsigned long long* device_buffer) { g_fwd16_stamps = device_buffer; }
+#endif
 
 extern "C" int topo_sccn_combine_fwd_tc2(const topo_combine_params* p, int64_t rows, const int32_t* n_rows_dev,
                                          float* out, topo_stream_t stream) {

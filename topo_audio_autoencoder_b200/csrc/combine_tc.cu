@@ -4,6 +4,10 @@
 #include <algorithm>
 
 #include "common.cuh"
+
+#ifndef TOPO_DEBUG_KERNELS
+#define TOPO_DEBUG_KERNELS 0
+#endif
 #include "tc.cuh"
 
 namespace topo {
@@ -582,6 +586,7 @@ __global__ void __launch_bounds__(128 * NQ, 1) combine_bwd_conv_tc_kernel(topo_c
 
 using namespace topo;
 
+#if TOPO_DEBUG_KERNELS      // unit-test GEMM: only in libtopo_b200_debug.so
 extern "C" int topo_debug_gemm_tf32x3(const float* a, const float* w, int64_t rows, int mode, float* out,
                                       topo_stream_t stream) {
     TOPO_REQUIRE(a && w && out && rows >= 0, "bad argument");
@@ -594,6 +599,7 @@ extern "C" int topo_debug_gemm_tf32x3(const float* a, const float* w, int64_t ro
     TOPO_LAUNCH_CHECK();
     return TOPO_OK;
 }
+#endif  // TOPO_DEBUG_KERNELS
 
 extern "C" int topo_sccn_combine_fwd_tc(const topo_combine_params* p, int64_t rows, const int32_t* n_rows_dev,
                                         float* out, topo_stream_t stream) {

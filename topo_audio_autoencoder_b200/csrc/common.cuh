@@ -66,6 +66,18 @@ struct topo_tables {
 };
 
 namespace topo {
+// The tables live on the device that was current when they were created: refuse a launch from any other device
+// instead of dereferencing foreign pointers (one ConstraintMatrices per device; nn.Module.to() does not move them).
+inline bool tables_on_current_device(const topo_tables* t) {
+    int dev = -1;
+    cudaGetDevice(&dev);
+    return t->device >= 0 && t->device == dev;
+}
+}  // namespace topo
+#define TOPO_REQUIRE_TABLES_DEVICE(t) \
+    TOPO_REQUIRE(::topo::tables_on_current_device(t), "the tables were uploaded to another device (or built host-only): create them on the current device")
+
+namespace topo {
 
 // ---- device helpers ----
 __device__ __forceinline__ float warp_sum(float v) {

@@ -164,6 +164,7 @@ __global__ void __launch_bounds__(128) operators_bwd_kernel(DeviceTables d, cons
 
 int check_common(const topo_tables* t, int64_t max_rows) {
     TOPO_REQUIRE(t != nullptr, "tables is null");
+    TOPO_REQUIRE_TABLES_DEVICE(t);
     TOPO_REQUIRE(max_rows >= 1, "max_rows must be >= 1");
     if (t->d.adj_w[0] < 0) {
         set_error("operator builder tables were not built for this vertex count (too large)");

@@ -288,6 +288,7 @@ using namespace topo;
 extern "C" int topo_rectify_fwd(const topo_tables* t, const float* probs_in, float eps, int64_t batch,
                                 float* probs_out, topo_stream_t stream) {
     TOPO_REQUIRE(t && probs_in && probs_out, "null argument");
+    TOPO_REQUIRE_TABLES_DEVICE(t);
     TOPO_REQUIRE(batch >= 0 && batch < (1 << 24), "bad batch");
     TOPO_REQUIRE(probs_in != probs_out, "in-place rectification is not supported");
     if (batch == 0) return TOPO_OK;
@@ -306,6 +307,7 @@ extern "C" int topo_rectify_bwd(const topo_tables* t, const float* probs_in, con
                                 const float* grad_out, float eps, int64_t batch, float* grad_in, float* workspace,
                                 topo_stream_t stream) {
     TOPO_REQUIRE(t && probs_in && probs_out && grad_out && grad_in && workspace, "null argument");
+    TOPO_REQUIRE_TABLES_DEVICE(t);
     TOPO_REQUIRE(batch >= 0 && batch < (1 << 24), "bad batch");
     if (batch == 0) return TOPO_OK;
     const DeviceTables& d = t->d;
@@ -339,6 +341,7 @@ extern "C" int topo_rectify_bwd(const topo_tables* t, const float* probs_in, con
 extern "C" int topo_active_sets(const topo_tables* t, const float* probs, int64_t batch, int32_t* pos,
                                 int32_t* act_idx, int32_t* counts, int32_t* row_off, topo_stream_t stream) {
     TOPO_REQUIRE(t && probs && pos && act_idx && counts && row_off, "null argument");
+    TOPO_REQUIRE_TABLES_DEVICE(t);
     TOPO_REQUIRE(batch >= 0 && batch <= 65535, "batch must be in [0, 65535]");
     if (batch == 0) return TOPO_OK;
     cudaStream_t s = as_stream(stream);
@@ -352,6 +355,7 @@ extern "C" int topo_penalties_fwd(const topo_tables* t, const float* probs, int6
                                   float max_active, float* vertex_penalty, float* entropy_loss,
                                   topo_stream_t stream) {
     TOPO_REQUIRE(t && probs && vertex_penalty && entropy_loss, "null argument");
+    TOPO_REQUIRE_TABLES_DEVICE(t);
     TOPO_REQUIRE(batch >= 0, "bad batch");
     if (batch == 0) return TOPO_OK;
     penalties_fwd_kernel<<<static_cast<unsigned>(batch), 128, 0, as_stream(stream)>>>(
@@ -364,6 +368,7 @@ extern "C" int topo_penalties_bwd(const topo_tables* t, const float* probs, int6
                                   float max_active, const float* g_vp, const float* g_ent, float* grad_probs,
                                   topo_stream_t stream) {
     TOPO_REQUIRE(t && probs && grad_probs, "null argument");
+    TOPO_REQUIRE_TABLES_DEVICE(t);
     TOPO_REQUIRE(batch >= 0, "bad batch");
     if (batch == 0) return TOPO_OK;
     penalties_bwd_kernel<<<static_cast<unsigned>(batch), 128, 0, as_stream(stream)>>>(

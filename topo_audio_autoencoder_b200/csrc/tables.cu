@@ -16,24 +16,31 @@ static thread_local std::string g_last_error;
 void set_error(const std::string& msg) { g_last_error = msg; }
 
 int sm_count() {
-    static int cached = 0;
-    if (cached == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev);
-        if (cached <= 0) cached = 148;
+    // per device: a process may drive more than one GPU
+    static int cached[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const int slot = dev >= 0 && dev < 64 ? dev : 0;
+    if (cached[slot] == 0) {
+        int n = 0;
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        cached[slot] = n > 0 ? n : 148;
     }
-    return cached;
+    return cached[slot];
 }
 
 int ensure_dynamic_smem(const void* kernel, size_t bytes) {
+    // cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute: the opt-in is recorded per (device, kernel)
     static std::mutex mu;
-    static std::map<const void*, size_t> done;
+    static std::map<std::pair<int, const void*>, size_t> done;
+    int dev = 0;
+    cudaGetDevice(&dev);
     std::lock_guard<std::mutex> lock(mu);
-    auto it = done.find(kernel);
+    const auto key = std::make_pair(dev, kernel);
+    auto it = done.find(key);
     if (it != done.end() && it->second >= bytes) return TOPO_OK;
     TOPO_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes)));
-    done[kernel] = bytes;
+    done[key] = bytes;
     return TOPO_OK;
 }
 
@@ -268,6 +275,7 @@ extern "C" int topo_tables_cofaces(const topo_tables* t, int rank, int32_t* host
 
 extern "C" int topo_tables_face_matrix(const topo_tables* t, int rank, float* dev_out, topo_stream_t stream) {
     TOPO_REQUIRE(t && dev_out, "null argument");
+    TOPO_REQUIRE_TABLES_DEVICE(t);
     TOPO_REQUIRE(rank >= 1 && rank <= 3, "rank out of range");
     const int rows = t->d.cnt[rank], cols = t->d.cnt[rank - 1];
     if (rows == 0 || cols == 0) return TOPO_OK;

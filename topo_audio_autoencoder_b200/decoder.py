@@ -1,0 +1,161 @@
+"""Drop-in for the reference's ``decoder.py``: the consumer of the complex stage's output.
+
+Reference: decoder.py:19-175.  ``AudioDecoder`` keeps the constructor, attribute names (state-dict compatible) and the
+``forward(feature_embeddings, complex_matrices, desired_length)`` signature; its ``sccn`` is this package's
+``GradientSCCN`` (csrc kernels).  The tail itself -- vertex->query MLP, temporal conv, cross-attention, upsampling --
+stays stock PyTorch, as the reference has it and the north star asks.
+
+What is this repo's own is the BATCHED consumer, ``DecoderTail.forward_batched``: it reads the compact per-rank rows the
+stage emits for a whole batch (inactive simplices are absent, samples concatenated, ``row_off`` marks the sample borders)
+and reproduces decoder.py:131-167 per sample without a Python loop over samples:
+  * row-wise layers (x0.1, vertex_to_query, pre-attention LayerNorm, key / value projections) run once over all rows;
+  * the temporal conv + interpolation along the vertex axis depend on a sample's active-vertex count, so samples are
+    grouped by that count (at most n_vertices + 1 groups; one group when every vertex is active);
+  * the rank 1-3 rows of a sample become its attention memory, padded to the longest sample with a key-padding mask.
+An inactive row must never reach the memory: the compaction contract is checked by tests/test_gpu_decoder.py.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .custom_sccn import GradientSCCN
+
+
+class ScaleLayer(nn.Module):
+    """reference decoder.py:177-183."""
+
+    def __init__(self, scale_factor):
+        super().__init__()
+        self.scale_factor = scale_factor
+
+    def forward(self, x):
+        return x * self.scale_factor
+
+
+class DecoderTail(nn.Module):
+    """Everything of reference ``AudioDecoder`` except ``self.sccn`` (decoder.py:31-108, 131-175)."""
+
+    def __init__(self, sccn_hidden_dim: int = 64, initial_sequence_length: int = 250, output_channels: int = 16):
+        super().__init__()
+        h = sccn_hidden_dim
+        self.hidden = h
+        self.initial_sequence_length = initial_sequence_length
+        self.vertex_to_query = nn.Sequential(nn.Linear(h, h * 2), nn.LayerNorm(h * 2), nn.GELU(),              # :34-41
+                                             nn.Linear(h * 2, h), nn.LayerNorm(h), nn.GELU())
+        self.temporal_conv = nn.Sequential(nn.Conv1d(h, h, kernel_size=3, padding=1, groups=8), nn.GroupNorm(8, h), nn.GELU(),   # :44-51
+                                           nn.Conv1d(h, h, kernel_size=3, padding=1, groups=8), nn.GroupNorm(8, h), nn.GELU())
+        self.pre_attention_norm = nn.LayerNorm(h)                                                              # :54-55
+        self.post_attention_norm = nn.LayerNorm(h)
+        self.cross_attention = nn.MultiheadAttention(embed_dim=h, num_heads=4, batch_first=True, dropout=0.0)  # :58-63
+        self.attention_scale = nn.Parameter(torch.ones(1) * 0.5)                                               # :66
+        mid = h // 2
+        self.key_proj = nn.Sequential(nn.Linear(h, mid), nn.LayerNorm(mid), nn.GELU(), nn.Linear(mid, h), nn.LayerNorm(h))   # :70-83
+        self.value_proj = nn.Sequential(nn.Linear(h, mid), nn.LayerNorm(mid), nn.GELU(), nn.Linear(mid, h), nn.LayerNorm(h))
+        channels = [h, h // 2, h // 4, output_channels]                                                        # :86-105
+        self.upsample_blocks = nn.ModuleList()
+        for i in range(4):
+            cin, cout = channels[i], channels[min(i + 1, len(channels) - 1)]
+            self.upsample_blocks.append(nn.Sequential(
+                nn.Upsample(scale_factor=2, mode="linear", align_corners=False),
+                nn.Conv1d(cin, cin, kernel_size=3, padding=1, groups=cin), nn.Conv1d(cin, cout, kernel_size=1),
+                nn.GroupNorm(min(8, cout), cout), nn.GELU(), ScaleLayer(1.0 / (2 ** (i + 1)))))
+        self.apply(self._init_weights)                                                                         # :108
+
+    @staticmethod
+    def _init_weights(m):                                                                                      # :110-118
+        if isinstance(m, (nn.Linear, nn.Conv1d)):
+            nn.init.kaiming_normal_(m.weight, mode="fan_in", nonlinearity="linear")
+            if m.bias is not None:
+                nn.init.zeros_(m.bias)
+
+    # ---- one sample, the reference's own order of operations (decoder.py:131-175) ----------------------------
+    def attend(self, output: Dict[str, Optional[torch.Tensor]]) -> torch.Tensor:
+        v = self.vertex_to_query(output["rank_0"] * 0.1)                                                       # :132-133
+        q = self.temporal_conv(v.transpose(0, 1).unsqueeze(0))                                                 # :136-137
+        q = F.interpolate(q, size=self.initial_sequence_length, mode="linear", align_corners=False).transpose(1, 2)   # :140-141
+        mem = [output[f"rank_{r}"] * 0.1 for r in range(1, 4) if output.get(f"rank_{r}") is not None]          # :144-150
+        mem = self.pre_attention_norm(torch.cat(mem, dim=0).unsqueeze(0))                                      # :153-156
+        q = self.pre_attention_norm(q)
+        a, _ = self.cross_attention(query=q, key=self.key_proj(mem), value=self.value_proj(mem))               # :158-162
+        return self.post_attention_norm(q + F.gelu(a * self.attention_scale))                                  # :163-167
+
+    def upsample(self, x: torch.Tensor) -> torch.Tensor:
+        x = x.transpose(1, 2)                                                                                  # :170
+        for block in self.upsample_blocks:
+            x = block(x)
+        return x
+
+    def forward(self, output: Dict[str, Optional[torch.Tensor]]) -> torch.Tensor:
+        return self.upsample(self.attend(output))
+
+    # ---- a whole batch of compact rows -----------------------------------------------------------------------
+    def attend_batched(self, xs: Sequence[torch.Tensor], counts: torch.Tensor) -> torch.Tensor:
+        """xs[r]: [sum_b counts[b, r], C] compact rows of rank r, samples concatenated (rows past the total are
+        ignored); counts: [B, 4] HOST tensor of active rows per sample and rank.  -> [B, L, C]."""
+        counts = counts.to("cpu", torch.int64)
+        b, dev, h = counts.shape[0], xs[0].device, self.hidden
+        tot = counts.sum(dim=0).tolist()
+        if int(counts[:, 0].min()) == 0:
+            raise ValueError("a sample without active vertices has no decoder input (the reference returns None, "
+                             "audio2complex.py:47-48); filter empty complexes before the decoder")
+        mem_len = counts[:, 1:].sum(dim=1)
+        if int(mem_len.min()) == 0:
+            raise ValueError("a sample without any active edge, triangle or tetrahedron has no attention memory "
+                             "(decoder.py:153 would concatenate an empty list)")
+        # queries: row-wise MLP over all vertex rows, then per group of equal vertex count
+        v = self.vertex_to_query(xs[0][:tot[0]] * 0.1)
+        starts0 = torch.cumsum(counts[:, 0], 0) - counts[:, 0]
+        q = torch.empty(b, self.initial_sequence_length, h, dtype=v.dtype, device=dev)
+        for n0 in torch.unique(counts[:, 0]).tolist():
+            members = torch.nonzero(counts[:, 0] == n0).squeeze(1)
+            idx = (starts0[members].unsqueeze(1) + torch.arange(n0).unsqueeze(0)).to(dev)                    # [g, n0]
+            grp = v[idx].transpose(1, 2)                                                                       # [g, C, n0]
+            grp = F.interpolate(self.temporal_conv(grp), size=self.initial_sequence_length, mode="linear", align_corners=False)
+            q[members.to(dev)] = grp.transpose(1, 2)
+        q = self.pre_attention_norm(q)
+        # memory: the rank 1..3 rows of every sample, in rank order, padded to the longest sample
+        rows = torch.cat([xs[r][:tot[r]] for r in (1, 2, 3)], dim=0) * 0.1
+        rows = self.pre_attention_norm(rows)
+        keys, values = self.key_proj(rows), self.value_proj(rows)
+        m_max = int(mem_len.max())
+        base = [0, tot[1], tot[1] + tot[2]]
+        starts = [torch.cumsum(counts[:, r], 0) - counts[:, r] for r in (1, 2, 3)]
+        sample_of, slot_of, src = [], [], []
+        offset_in_sample = torch.zeros(b, dtype=torch.int64)
+        for j, r in enumerate((1, 2, 3)):
+            c = counts[:, r]
+            sid = torch.repeat_interleave(torch.arange(b), c)
+            within = torch.arange(int(c.sum())) - torch.repeat_interleave(starts[j], c)
+            sample_of.append(sid)
+            slot_of.append(offset_in_sample[sid] + within)
+            src.append(base[j] + torch.arange(int(c.sum())))
+            offset_in_sample = offset_in_sample + c
+        sample_of, slot_of, src = (torch.cat(t).to(dev) for t in (sample_of, slot_of, src))
+        k_pad = keys.new_zeros(b, m_max, h)
+        v_pad = values.new_zeros(b, m_max, h)
+        k_pad[sample_of, slot_of] = keys[src]
+        v_pad[sample_of, slot_of] = values[src]
+        pad_mask = (torch.arange(m_max).unsqueeze(0) >= mem_len.unsqueeze(1)).to(dev)
+        a, _ = self.cross_attention(query=q, key=k_pad, value=v_pad, key_padding_mask=pad_mask, need_weights=False)
+        return self.post_attention_norm(q + F.gelu(a * self.attention_scale))
+
+    def forward_batched(self, xs: Sequence[torch.Tensor], counts: torch.Tensor) -> torch.Tensor:
+        """-> [B, output_channels, 16 L] band signals (decoder.py:170-175)."""
+        return self.upsample(self.attend_batched(xs, counts))
+
+
+class AudioDecoder(DecoderTail):
+    """reference decoder.py:19-175, same signature.  ``forward`` takes one sample's embeddings and sparse operators."""
+
+    def __init__(self, sccn_hidden_dim: int = 64, initial_sequence_length: int = 250, output_channels: int = 16):
+        super().__init__(sccn_hidden_dim, initial_sequence_length, output_channels)
+        self.sccn = GradientSCCN(channels=sccn_hidden_dim, max_rank=3, n_layers=6, update_func="gelu")      # :25-30
+        self.sccn.apply(self._init_weights)          # the reference's self.apply (:108) also reaches the SCCN's Linear layers
+
+    def forward(self, feature_embeddings, complex_matrices, desired_length=None):
+        output = self.sccn(feature_embeddings, complex_matrices.incidences, complex_matrices.adjacencies)    # :129
+        return DecoderTail.forward(self, output)

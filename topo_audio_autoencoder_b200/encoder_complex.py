@@ -145,7 +145,7 @@ class _PenaltiesFn(torch.autograd.Function):
 class ComplexHead(nn.Module):
     """Complex-generation state and methods of the reference AudioEncoder (see module docstring)."""
 
-    def __init__(self, num_vertices: int, embedding_dim: int = 128, min_active_vertices: int = 8,
+    def __init__(self, num_vertices: int, embedding_dim: int = 64, min_active_vertices: int = 8,
                  max_active_vertices: int = 16, gate: str = "hard_concrete", bias_on: str = "logits",
                  start_temp: float = 2.0 / 3.0, ste: bool = False):
         super().__init__()
@@ -178,6 +178,15 @@ class ComplexHead(nn.Module):
         for name, n in zip(names, sizes):                                  # encoder.py:177-195
             setattr(self, name, nn.Sequential(nn.Embedding(max(n, 1), embedding_dim), nn.LayerNorm(embedding_dim)))
         self._embedding_names = names
+
+    def _apply(self, fn, *args, **kwargs):
+        """nn.Module.to() / .cuda(): the static tables are device memory owned by libtopo_b200, not parameters or
+        buffers, so they are re-created on the device the parameters moved to."""
+        out = super()._apply(fn, *args, **kwargs)
+        dev = self.vertex_bias.device
+        if dev.type == "cuda" and dev != self.constraints._tables.device:
+            self.constraints = ConstraintMatrices.create(self.num_vertices, device=dev)
+        return out
 
     # ---- reference methods -------------------------------------------------------------------
     @property
@@ -226,7 +235,10 @@ class ComplexHead(nn.Module):
         host_counts = None
         if sync:
             host_counts = counts.cpu()
-            rows_max = [int(v) for v in host_counts.sum(dim=0).tolist()]
+            # exact totals, but never a zero-size buffer: a rank without a single live row in the whole batch (say no
+            # tetrahedron survived the gate) keeps one dead row so that every kernel still receives a valid pointer;
+            # the device-side live count of that rank is 0 and no kernel touches the row
+            rows_max = [max(int(v), 1) for v in host_counts.sum(dim=0).tolist()]
         return BatchedComplex(tables=t, probs=rectified, pos=pos, act_idx=act, counts=counts, row_off=row_off,
                               rows_max=rows_max, host_counts=host_counts)
 
@@ -306,4 +318,5 @@ class ComplexStage(nn.Module):
     def split_per_sample(cx: BatchedComplex, x: torch.Tensor, rank: int) -> List[torch.Tensor]:
         if cx.host_counts is None:
             raise ValueError("split_per_sample needs forward(..., sync=True)")
-        return list(torch.split(x, cx.host_counts[:, rank].tolist(), dim=0))
+        sizes = cx.host_counts[:, rank].tolist()
+        return list(torch.split(x[:sum(sizes)], sizes, dim=0))        # rows past the live total are allocation slack

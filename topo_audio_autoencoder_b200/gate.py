@@ -69,17 +69,30 @@ class HardConcrete(nn.Module):
         super().__init__()
         self.offsets = [int(o) for o in offsets]
         self.start_temp, self.min_temp = start_temp, min_temp
-        self.current_temp = start_temp
+        # the annealed temperature lives in DEVICE memory (a non-persistent buffer that follows .to()): a CUDA graph that
+        # captured the gate then reads the value of the moment of each replay, not of the capture
+        self.register_buffer("_temp_buf", torch.tensor([float(start_temp)]), persistent=False)
+        self._temp_host = float(start_temp)
         self.ste = ste
         self.log_temp_scale = nn.Parameter(torch.zeros(1))
         self.gamma = nn.Parameter(torch.tensor([float(gamma)]))
         self.zeta = nn.Parameter(torch.tensor([float(zeta)]))
 
+    @property
+    def current_temp(self) -> float:
+        return self._temp_host
+
+    @current_temp.setter
+    def current_temp(self, value: float) -> None:
+        """trainer.py:266 assigns this attribute every epoch: the write lands in the device buffer (one fill kernel)."""
+        self._temp_host = float(value)
+        self._temp_buf.fill_(float(value))
+
     def set_temperature(self, temp: float) -> None:
         self.current_temp = max(float(temp), self.min_temp)
 
     def pack_params(self, loc: Optional[torch.Tensor]) -> torch.Tensor:
-        beta = self.current_temp * torch.exp(self.log_temp_scale)
+        beta = self._temp_buf * torch.exp(self.log_temp_scale)
         if loc is None:
             loc = torch.zeros(4, dtype=torch.float32, device=beta.device)
         return torch.cat([beta, self.gamma, self.zeta, loc.reshape(4)]).to(torch.float32)

@@ -18,6 +18,12 @@ class GraphedStep:
 
     After ``replay(logits, noise)``: ``outputs`` holds the stage's output tensors (static buffers),
     ``logits_grad`` the gradient w.r.t. the logits and every parameter's ``.grad`` is updated in place.
+
+    Python-side state and the graph.  Read from device memory at every replay (never baked in): parameters, inputs,
+    upstream gradients, the Hard Concrete temperature (``HardConcrete._temp_buf``).  Baked in at capture, because they are
+    by-value kernel arguments or shape decisions: the BinaryGumbel temperature, ``training`` / ``ste`` flags, LayerNorm
+    epsilons, the penalty bounds, the batch size.  ``replay`` compares these with their captured values and re-captures
+    the graph when one changed (the reference's trainer anneals the temperature once per epoch, trainer.py:266).
     """
 
     def __init__(self, stage, logits: torch.Tensor, noise: Optional[torch.Tensor], upstream: Sequence[torch.Tensor],
@@ -27,10 +33,22 @@ class GraphedStep:
         self.logits = logits.detach().clone().requires_grad_(True)
         self.noise = None if noise is None else noise.detach().clone()
         self.upstream = [u.detach().clone() for u in upstream]
-        self.graph = torch.cuda.CUDAGraph()
         self.outputs: Dict[str, torch.Tensor] = {}
         self.logits_grad: Optional[torch.Tensor] = None
+        self.captures = 0
+        self._capture(warmup)
 
+    def _baked_state(self):
+        """Everything the captured launches hold by value."""
+        head = self.stage.head
+        return (float(head.gumbel.current_temp), bool(self.stage.training), bool(head.sampler.ste), head.gate_kind, head.bias_on,
+                float(head.min_active_vertices), float(head.max_active_vertices),
+                tuple(bool(layer.training) for layer in self.stage.sccn.layers))
+
+    def _capture(self, warmup: int = 1):
+        self.graph = torch.cuda.CUDAGraph()
+        self._baked = self._baked_state()
+        self.captures += 1
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):          # warm-up off the capture: allocator, function attributes
@@ -62,6 +80,8 @@ class GraphedStep:
             self.logits.data.copy_(logits, non_blocking=True)
         if noise is not None and self.noise is not None:
             self.noise.copy_(noise, non_blocking=True)
+        if self._baked_state() != self._baked:          # e.g. BinaryGumbel.set_temperature between epochs
+            self._capture()
         self.graph.replay()
         for p, g in zip(self.params, self.param_grads):      # re-attach if the caller cleared or replaced .grad
             p.grad = g

@@ -110,6 +110,30 @@ class BatchAudioDistance(nn.Module):
         return {"spectral_distance": torch.diagonal(block).clone()}
 
 
+def load_wav(path) -> torch.Tensor:
+    """One audio file -> float32 [channels, T] in [-1, 1), as ``torchaudio.load`` returns it (reference :77).  torchaudio
+    needs an audio backend (torchcodec / soundfile) that is not always installed; 16-bit and 32-bit PCM and float32 wav
+    files are then read with the standard library instead."""
+    try:
+        import torchaudio
+        wav, _ = torchaudio.load(path)
+        return wav
+    except (ImportError, RuntimeError, OSError):
+        pass
+    import wave
+    import numpy as np
+    with wave.open(str(path), "rb") as w:
+        ch, width, frames = w.getnchannels(), w.getsampwidth(), w.getnframes()
+        raw = w.readframes(frames)
+    if width == 2:
+        x = np.frombuffer(raw, dtype="<i2").astype(np.float32) / 32768.0
+    elif width == 4:
+        x = np.frombuffer(raw, dtype="<i4").astype(np.float32) / 2147483648.0
+    else:
+        raise ValueError(f"{path}: unsupported sample width {width} bytes")
+    return torch.from_numpy(x.reshape(-1, ch).T.copy())
+
+
 def neighbour_order(distances: torch.Tensor):
     """reference :121-126: full ascending order of every row, self dropped."""
     vals, idx = torch.sort(distances, dim=1)
@@ -120,13 +144,12 @@ def compute_distances(audio_dir: Path, save_path: Path, batch_size: int = 32):
     """reference :51-153.  Same inputs and the same two output files (distance_matrix.pt,
     neighbors.pkl with 'sorted_neighbors' / 'sorted_distances' / 'index' per file and the
     '__file_to_idx__' map); ``batch_size`` is accepted for signature parity and unused."""
-    import torchaudio
     audio_files = list(Path(audio_dir).glob("*.wav"))
     n_files = len(audio_files)
     file_to_idx = {str(f): i for i, f in enumerate(audio_files)}
     wavs, max_len = [], 0
     for f in audio_files:
-        wav, _ = torchaudio.load(f)
+        wav = load_wav(f)
         wavs.append(wav.unsqueeze(0))
         max_len = max(max_len, wav.shape[-1])
     audio = torch.cat([torch.nn.functional.pad(w, (0, max_len - w.shape[2])) for w in wavs], dim=0).cuda()

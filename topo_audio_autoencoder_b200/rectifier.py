@@ -91,10 +91,25 @@ class ConstraintMatrices:
             if v2e is None:
                 raise ValueError("ConstraintMatrices needs either dense matrices or ConstraintMatrices.create(n)")
             _tables = _Tables(v2e.shape[1])
+            # the kernels walk the canonical face tables of the complete 3-skeleton: a hand-built instance is accepted
+            # only if it describes that same complex (anything else would be silently ignored otherwise)
+            canon = (None, _tables.simplex_vertices(1), _tables.simplex_vertices(2), _tables.simplex_vertices(3))
+            for rank, (dense, idx) in enumerate(((v2e, indices.edges), (e2t, indices.triangles), (t2tt, indices.tetra)), start=1):
+                if idx is not None and not torch.equal(idx.reshape(-1, rank + 1).cpu().to(torch.int64), canon[rank]):
+                    raise ValueError(f"ConstraintMatrices: rank-{rank} index list is not the complete skeleton in "
+                                     "itertools.combinations order; only ConstraintMatrices.create(n)'s complex is supported")
+                if dense is not None and not torch.equal(dense.to(_tables.device, torch.float32), _tables.face_matrix(rank)):
+                    raise ValueError(f"ConstraintMatrices: rank-{rank} face matrix differs from the canonical 0/1 face "
+                                     "matrix; only ConstraintMatrices.create(n)'s complex is supported")
         self._tables = _tables
 
     @classmethod
-    def create(cls, n_vertices: int) -> "ConstraintMatrices":
+    def create(cls, n_vertices: int, device=None) -> "ConstraintMatrices":
+        """``device``: the CUDA device the static tables are uploaded to (default: the current one).  The tables do not
+        follow ``nn.Module.to()``; owners re-create them when they move (ComplexHead._apply)."""
+        if device is not None:
+            with torch.cuda.device(device):
+                return cls.create(n_vertices)
         tables = _Tables(n_vertices)
         dev = tables.device
         indices = SimplexIndices(edges=tables.simplex_vertices(1).to(dev),
