@@ -9,22 +9,19 @@ reference`` legs do, and only as the checker or the timed CPU arm.
 
 Pinning status (see DESIGN.md "Oracle"):
 
-* ``rectifier_oracle``, ``complex_builder_oracle``: PINNED.  Checked bit for bit
-  against the unmodified reference ``rectifier.py`` / ``complex_builder.py``
-  (importable in the authoring container) by ``oracle/make_golden.py``; the
-  resulting vectors are committed under ``tests/golden/``.
-* ``glue_oracle`` (split / active embeddings / penalties): restated from
-  ``encoder.py``; the functions are pure torch but the module cannot be imported
-  (unused ``toponetx`` import), so they are pinned only by reading.
-* ``gate_oracle.binary_gumbel_train``: restated from ``encoder.py:33-41`` with
-  the Gumbel noise injected.  ``gate_oracle.hard_concrete``: PARITY UNPINNED --
-  the reference contains no Hard Concrete code (README prose only); the spec is
-  the builder's, after Louizos et al. 2018.
-* ``sccn_oracle``: PARITY UNPINNED -- the arithmetic of ``Conv`` lives in
-  TopoModelX (pyt-team/TopoModelX, path-imported, no version pinned, absent from
-  the machine).  ``custom_sccn.py:62-138`` is restated on a stand-in
-  ``Conv = neighborhood @ (x @ W)``.
-* ``distance_oracle``: the pair reduction (``precompute_distances.py:11-49``) is
-  pinned by reading; ``MultiScaleSTFT`` is acids-rave (absent, unpinned) and is
-  restated with ``torch.stft``.
+* ``rectifier_oracle``, ``complex_builder_oracle``: PINNED.  Checked bit for bit against the unmodified reference
+  ``rectifier.py`` / ``complex_builder.py`` by ``oracle/make_golden.py``; vectors under ``tests/golden/``.
+* ``glue_oracle`` (split / active embeddings / penalties), ``gate_oracle.binary_gumbel_train``,
+  ``distance_oracle`` (everything after the STFT, including ``compute_distances`` and its two output files),
+  ``sccn_oracle`` (the whole forward body of ``GradientSCCNLayer`` / ``GradientSCCN``) and ``decoder_oracle`` (the
+  consumer of the SCCN output): PINNED.  ``oracle/make_golden_glue.py`` imports the unmodified reference
+  ``encoder.py`` / ``precompute_distances.py`` / ``custom_sccn.py`` / ``decoder.py`` with the stub modules of
+  ``oracle/_ref_stubs.py`` for the three absent third-party packages, runs the reference's own code and asserts the
+  restatements reproduce it bit for bit; vectors ``tests/golden/ref_*.npz``.
+* Still UNPINNED, because the code is not on this machine or does not exist:
+  - ``Conv`` arithmetic (TopoModelX, pyt-team/TopoModelX, path-imported, no version pinned): stand-in
+    ``neighborhood @ (x @ W)`` on both sides of every comparison;
+  - ``MultiScaleSTFT`` (acids-rave): restated with ``torch.stft`` (Hann, hop = scale / 4, centred, reflect, magnitude);
+  - ``gate_oracle.hard_concrete``: the reference contains no Hard Concrete code (README prose only); the spec is the
+    builder's, after Louizos et al. 2018.
 """

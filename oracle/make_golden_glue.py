@@ -427,7 +427,9 @@ def gen_sccn():
                                               {"rank_0": rnd_sparse(n0, n0, 5), "rank_1": rnd_sparse(n1, n1, 5)}, 101)
 
     # (2) a real sparse complex from the reference's own rectifier + builder, all four ranks, train and eval
-    pl, act, built = real_complex(7, 9001)
+    pl, act, built = real_complex(7, 9001, p_zero=0.06)
+    assert all(len(act[k]) > 0 for k in NAMES), {k: len(act[k]) for k in NAMES}
+    assert all(len(act[k]) < full for k, full in zip(NAMES, (7, 21, 35, 35))), "some simplices of every rank must be inactive"
     g = torch.Generator().manual_seed(43)
     feats = {f"rank_{r}": torch.randn(len(act[k]), ch, generator=g) * pl[r][act[k]].unsqueeze(1) for r, k in enumerate(NAMES)}
     inc = {k: v.detach() for k, v in built.incidences.items()}
@@ -442,10 +444,20 @@ def gen_sccn():
     adj3 = dict(adj); adj3["rank_1"] = None; adj3.pop("rank_3")
     cases["ref_sccn_missing_ranks"] = sccn_case("missing_ranks", ch, 3, 2, True, feats3, inc3, adj3, 104)
 
-    # (4) small channel count (the any-C FFMA path on the GPU), three layers
+    # (3b) the two highest ranks empty (no triangle survives): zero-row features and zero-entry operators, as the
+    #      reference's generate_complex hands them over (encoder.py:373-384)
+    pl0, act0, built0 = real_complex(7, 9001, p_zero=0.3)
+    assert len(act0["triangles"]) == 0 and len(act0["tetra"]) == 0 and len(act0["edges"]) > 0
+    g = torch.Generator().manual_seed(45)
+    feats0 = {f"rank_{r}": torch.randn(len(act0[k]), ch, generator=g) for r, k in enumerate(NAMES)}
+    cases["ref_sccn_empty_high_ranks"] = sccn_case("empty_high_ranks", ch, 3, 2, True, feats0,
+                                                   {k: v.detach() for k, v in built0.incidences.items()},
+                                                   {k: v.detach() for k, v in built0.adjacencies.items()}, 106)
+
+    # (4) another channel count (the any-C FFMA combine on the GPU; its SpMM is instantiated for 32 / 64 / 128), three layers
     g = torch.Generator().manual_seed(44)
-    feats16 = {f"rank_{r}": torch.randn(len(act[k]), 16, generator=g) for r, k in enumerate(NAMES)}
-    cases["ref_sccn_complex7_c16"] = sccn_case("complex7_c16", 16, 3, 3, True, feats16, inc, adj, 105)
+    feats32 = {f"rank_{r}": torch.randn(len(act[k]), 32, generator=g) for r, k in enumerate(NAMES)}
+    cases["ref_sccn_complex7_c32"] = sccn_case("complex7_c32", 32, 3, 3, True, feats32, inc, adj, 105)
     return cases
 
 

@@ -117,7 +117,9 @@ def test_distances_against_reference(tmp_path):
     ours_of_ref = [f2i[str(adir / name)] for name in order]           # reference row -> our row (glob order may differ)
     perm = torch.tensor(ours_of_ref)
     want = torch.from_numpy(fx["cd_matrix"])
-    assert_close("ref/compute-distances/matrix", got[perm][:, perm], want, rtol=2e-5, atol=1e-6)
+    # zero-padded clips: every pair carries |log(1e-7) - log(s)| terms of ~16 per bin, so the entries are ~100 and their
+    # fp32 sums over 10^5 bins agree to a few 1e-5 relative
+    assert_close("ref/compute-distances/matrix", got[perm][:, perm], want, rtol=5e-5, atol=1e-6)
     assert got.dtype == torch.float32 and tuple(got.shape) == (len(order), len(order))
     assert torch.equal(got, got.t()) and (torch.diagonal(got) == 0).all()
     for ref_row, name in enumerate(order):
@@ -126,7 +128,7 @@ def test_distances_against_reference(tmp_path):
         assert rec["index"] == ours_of_ref[ref_row]
         want_names = [str(adir / order[j]) for j in fx["cd_sorted_idx"][ref_row].tolist()]
         assert rec["sorted_neighbors"] == want_names, f"neighbour order of {name}"
-        np.testing.assert_allclose(rec["sorted_distances"], fx["cd_sorted_vals"][ref_row], rtol=2e-5, atol=1e-6)
+        np.testing.assert_allclose(rec["sorted_distances"], fx["cd_sorted_vals"][ref_row], rtol=5e-5, atol=1e-6)
 
 
 @pytest.mark.parametrize("case", ref_sccn_cases())
@@ -152,12 +154,16 @@ def test_sccn_against_reference_forward(case):
             assert_fp32_equivalent(f"ref/{case}/dx/{k}", g, torch.from_numpy(fx[f"gx_{k}"]), gf64[k])
     for (kind, k), g in gm.items():
         if f"g{kind}_{k}" in fx.files:
-            assert g is not None, (case, kind, k)
+            if g is None:               # an operator of an empty rank: the reference's gradient is an empty tensor
+                assert fx[f"g{kind}_{k}"].size == 0, (case, kind, k)
+                continue
             assert_fp32_equivalent(f"ref/{case}/d{kind}/{k}", g, torch.from_numpy(fx[f"g{kind}_{k}"]), gm64[(kind, k)])
     floor = 5e-6 * max(float(np.abs(fx[f]).max()) for f in fx.files if f.startswith("gp_"))
     for k, g in gp.items():
         if f"gp_{k}" in fx.files:
-            assert g is not None, (case, k)
+            if g is None:               # parameters of an empty rank: the reference reports an all-zero gradient
+                assert not fx[f"gp_{k}"].any(), (case, k)
+                continue
             assert_fp32_equivalent(f"ref/{case}/dparam/{k}", g, torch.from_numpy(fx[f"gp_{k}"]), gp64[k], floor=floor)
         else:
             assert g is None or g.abs().max().item() == 0, (case, k)

@@ -51,6 +51,8 @@ class CsrPattern:
 
 
 def _spmm_raw(row_ptr, col, vals, x, n_rows):
+    if n_rows == 0 or vals.numel() == 0 or x.shape[0] == 0:       # an empty rank or an operator without entries (the
+        return torch.zeros(n_rows, x.shape[1], dtype=torch.float32, device=x.device)   # reference multiplies empty tensors)
     y = torch.empty(n_rows, x.shape[1], dtype=torch.float32, device=x.device)
     check(lib.topo_spmm_csr(n_rows, ptr(row_ptr, torch.int32), ptr(col, torch.int32), ptr(vals), ptr(x),
                             x.shape[1], ptr(y), stream()))
@@ -74,6 +76,8 @@ class _SpmmFn(torch.autograd.Function):
         vals, x = ctx.saved_tensors
         p, g_y = ctx.pattern, g_y.contiguous()
         g_vals = torch.empty_like(vals)
+        if vals.numel() == 0 or x.shape[0] == 0 or g_y.shape[0] == 0:
+            return g_vals, torch.zeros_like(x), None, None
         if ctx.transposed:      # y = A^T x:  dx = A g_y ;  dA[i,j] = x[i] . g_y[j]
             g_x = _spmm_raw(p.row_ptr, p.col, vals, g_y, p.shape[0])
             check(lib.topo_sddmm_csr(p.shape[0], ptr(p.row_ptr, torch.int32), ptr(p.col, torch.int32), ptr(x),

@@ -250,8 +250,8 @@ class ComplexHead(nn.Module):
         flat, _ = self._flat((vertices, edges, triangles, tetra))
         cx = self.batched_complex(flat, sync=True)
         xs = self.embed(cx)
-        out = {f"rank_{r}": xs[r] for r in range(4)}
-        o, n = self._tables.offsets, cx.rows_max
+        o, n = self._tables.offsets, [int(v) for v in cx.host_counts[0].tolist()]
+        out = {f"rank_{r}": xs[r][:n[r]] for r in range(4)}        # an empty rank is [0, C], as the reference returns it
         out["active_indices"] = {key: cx.act_idx[0, o[r]:o[r] + n[r]].to(torch.int64) for r, key in enumerate(RANK_KEYS)}
         return out
 
