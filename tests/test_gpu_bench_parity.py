@@ -1,0 +1,121 @@
+"""GPU parity AT THE BENCHMARKED CONFIGURATION: 20 vertices (6,195 candidate simplices), C = 64, 6 SCCN layers, the step
+captured in a CUDA graph with the four rank launches of a layer side by side on SM partitions -- exactly what bench.py
+times -- against the per-clip oracle chain in fp32 and in fp64 (oracle/chain.py).
+
+Writes the tracked error table (gpurun_out/parity_r02_<regime>.md, copied to profiles/parity_r02.md): per tensor class
+max |err| against the fp32 oracle, whether the north star's strict element-wise bound (rtol 1e-5 / atol 1e-6) holds, and
+both fp32 results' distance to the fp64 answer.  Asserted: index sets and zero sets bit-exact; the strict bound where it
+can hold (gate, rectifier, penalties); for the 6-layer chain the fp64-anchored criterion of
+helpers.assert_fp32_equivalent (ours as close to fp64 as the oracle's own fp32 run, factor 4)."""
+import os
+
+import pytest
+import torch
+
+from oracle.chain import NAMES, stage_oracles
+from tests.helpers import ATOL, ROOT, RTOL, assert_close, assert_fp32_equivalent
+
+pytestmark = pytest.mark.gpu
+B = int(os.environ.get("TOPO_PARITY_BATCH", "16"))
+
+
+def _row(tag, got, o32, o64):
+    g, a, d = got.detach().double().cpu(), o32.detach().double().cpu(), o64.detach().double().cpu()
+    err = (g - a).abs()
+    strict = bool(((err - (ATOL + RTOL * a.abs())) <= 0).all())
+    scale = d.abs().max().item()
+    return (f"| {tag} | {g.numel()} | {scale:.3e} | {err.max().item():.3e} | {'yes' if strict else 'no'} | "
+            f"{(g - d).abs().max().item():.3e} | {(a - d).abs().max().item():.3e} |")
+
+
+@pytest.mark.parametrize("regime", ["full", "sparse"])
+def test_benchmarked_step_against_oracle_chain(regime):
+    import topo_audio_autoencoder_b200 as T
+    from topo_audio_autoencoder_b200 import custom_sccn as cs
+    from topo_audio_autoencoder_b200.graph import GraphedStep
+    assert cs.CONCURRENT_RANKS and cs.COMBINE_IMPL == "tc", "the benchmarked execution mode"
+    n, C, L = 20, 64, 6
+    gate, bias_on = ("binary_gumbel", "probs") if regime == "full" else ("hard_concrete", "logits")
+    torch.manual_seed(511990)
+    stage = T.ComplexStage(n, channels=C, n_layers=L, gate=gate, bias_on=bias_on).cuda().train()
+    N = stage.head.total_simplices
+    g = torch.Generator().manual_seed(511990)
+    logits = torch.randn(B, N, generator=g)
+    if regime == "full":
+        noise = -torch.empty(2, B, N).exponential_(generator=g).log()
+    else:
+        noise = torch.rand(B, N, generator=g).clamp_(1e-6, 1 - 1e-6)
+    counts = stage.head._tables.counts
+    ups = [torch.randn(B * c, C, generator=g) for c in counts]
+    up_vp, up_ent = torch.rand(B, generator=g) + 0.5, torch.rand(B, generator=g) + 0.5
+
+    graphed = GraphedStep(stage, logits.cuda(), noise.cuda(), [u.cuda() for u in ups] + [up_vp.cuda(), up_ent.cuda()])
+    out = graphed.replay(logits.cuda(), noise.cuda())
+    torch.cuda.synchronize()
+    got = {k: v.clone() for k, v in out.items()}
+    lg = graphed.logits_grad.clone()
+    grads = {name: (None if p.grad is None else p.grad.clone()) for name, p in stage.named_parameters()}
+    # second replay of the same inputs: parameter gradients leave the kernels through floating-point atomics
+    graphed.replay(logits.cuda(), noise.cuda())
+    torch.cuda.synchronize()
+    repro = max(((p.grad - grads[name]).abs().max().item() / max(grads[name].abs().max().item(), 1e-30))
+                for name, p in stage.named_parameters() if p.grad is not None)
+    assert torch.equal(graphed.logits_grad, lg), "d loss / d logits must be bit-reproducible (single-owner rows, no atomics)"
+
+    o32, o64 = stage_oracles(stage, gate, bias_on)
+    # the oracle's upstream rows follow ITS active sets; they equal ours (asserted below), so the compact buffers line up
+    rec32, dl32, loss32 = o32.run(logits, noise, ups, up_vp, up_ent)
+    rec64, dl64, loss64 = o64.run(logits, noise, ups, up_vp, up_ent)
+
+    off = o32.off
+    rect = got["rectified"].cpu()
+    lines = [f"## {regime}: n = {n}, C = {C}, L = {L}, B = {B}, CUDA graph, concurrent rank launches", "",
+             "| tensor | elements | max abs value (fp64) | max abs err vs fp32 oracle | strict 1e-5 / 1e-6 holds | ours - fp64 | "
+             "oracle fp32 - fp64 |", "|---|---:|---:|---:|---|---:|---:|"]
+    # ---- bit-exact parts ----
+    want_rect = torch.stack([r["rect"] for r in rec32])
+    assert torch.equal(rect == 0, want_rect == 0), "zero sets of the rectified probabilities"
+    outs32 = [[] for _ in range(4)]
+    outs64 = [[] for _ in range(4)]
+    for b in range(B):
+        for r in range(4):
+            idx = rec32[b]["active"][NAMES[r]]
+            mine = torch.nonzero(rect[b, off[r]:off[r + 1]]).squeeze(1)
+            assert torch.equal(mine, idx), f"active index set, clip {b} rank {r}"
+            outs32[r].append(rec32[b]["out"][r])
+            outs64[r].append(rec64[b]["out"][r])
+    lines.append(_row("rectified probabilities", rect, want_rect, torch.stack([r["rect"] for r in rec64])))
+    assert_close(f"bench-parity/{regime}/rectified", rect, want_rect)
+    vp32, ent32 = torch.stack([r["vp"] for r in rec32]), torch.stack([r["ent"] for r in rec32])
+    vp64, ent64 = torch.stack([r["vp"] for r in rec64]), torch.stack([r["ent"] for r in rec64])
+    lines.append(_row("vertex penalty", got["vertex_penalty"], vp32, vp64))
+    lines.append(_row("entropy loss", got["entropy_loss"], ent32, ent64))
+    assert_close(f"bench-parity/{regime}/vertex_penalty", got["vertex_penalty"], vp32)
+    assert_close(f"bench-parity/{regime}/entropy", got["entropy_loss"], ent32)
+    # ---- the 6-layer chain ----
+    for r in range(4):
+        a, d = torch.cat(outs32[r]), torch.cat(outs64[r])
+        mine = got[f"rank_{r}"][:a.shape[0]]
+        lines.append(_row(f"SCCN output rank {r}", mine, a, d))
+        assert_fp32_equivalent(f"bench-parity/{regime}/rank_{r}", mine, a, d)
+    lines.append(_row("d loss / d logits", lg, dl32, dl64))
+    assert_fp32_equivalent(f"bench-parity/{regime}/dlogits", lg, dl32, dl64)
+    g32, g64 = o32.named_grads(), o64.named_grads()
+    floor = 5e-6 * max(v.abs().max().item() for v in g64.values() if v is not None)
+    groups = {}
+    for name, gr in grads.items():
+        if gr is None or g32.get(name) is None:
+            continue
+        key = ("head: " + name.split(".")[1]) if name.startswith("head.") else "sccn: " + ".".join(name.split(".")[3:4])
+        groups.setdefault(key, []).append(name)
+        assert_fp32_equivalent(f"bench-parity/{regime}/d{name}", gr, g32[name], g64[name], floor=floor)
+    for key, names in sorted(groups.items()):
+        cat = lambda src: torch.cat([src[nm].reshape(-1).double().cpu() for nm in names])      # noqa: E731
+        lines.append(_row(f"parameter gradients, {key} ({len(names)} tensors)", cat(grads), cat(g32), cat(g64)))
+    lines += ["", f"Two replays of the same inputs: d loss / d logits bit-identical; parameter gradients differ by at most "
+                  f"{repro:.2e} of their largest entry (accumulated with `red.global.add`, order not fixed).", ""]
+    path = os.path.join(ROOT, "gpurun_out", f"parity_r02_{regime}.md")
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    with open(path, "w") as f:
+        f.write("\n".join(lines) + "\n")
+    assert repro < 1e-4
