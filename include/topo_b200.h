@@ -390,6 +390,16 @@ int topo_distance_rows(const float* spec_p, const float* logspec_p, const float*
                        const int64_t* host_seg_len, int n_scales, int64_t row_begin, int64_t row_end,
                        int64_t col_begin, int64_t col_end, float* out, topo_stream_t stream);
 
+/* One block of the sweep with rows and columns taken from DIFFERENT prepared blocks (streaming: a resident row block
+ * against column blocks prepared on the fly, precompute_distances.py:89-115 at collection sizes whose spectra do not fit
+ * in HBM).  row_* hold clips [row_global0, row_global0 + n_rows) of the collection, col_* clips [col_global0, ...); the
+ * collection-wide indices decide which clip of a pair is the lower one (its mean square is the normaliser, :106-110) and
+ * where the diagonal is.  out[i * ld_out + j], i < n_rows, j < n_cols. */
+int topo_distance_block(const float* row_spec, const float* row_logspec, const float* row_sq_mean, int64_t n_rows,
+                        int64_t row_global0, const float* col_spec, const float* col_logspec, const float* col_sq_mean,
+                        int64_t n_cols, int64_t col_global0, const int64_t* seg_len, int n_scales, float* out,
+                        int64_t ld_out, topo_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -509,9 +509,32 @@ def gen_decoder_tail():
     return fx
 
 
+# --------------------------------------------------------------------------------------------------
+# convolutional front-end (stock PyTorch in the reference; needed for the full training step only)
+# --------------------------------------------------------------------------------------------------
+def gen_frontend():
+    """encoder.py:390-426 cannot be called (forward goes on into generate_complex, which raises): the same
+    statements are executed here on the reference's own modules, in eval mode (dropout off)."""
+    seed, n = 301, 6
+    enc = ref_enc.AudioEncoder(num_vertices=n, embedding_dim=64)
+    fill_by_name(enc, seed)
+    enc.eval()
+    x = tensor_by_name(seed, "frontend_input", (2, 16, 4000), "normal", 0.3)
+    with torch.no_grad():
+        feats = torch.cat([bp(x[:, i:i + 1]) for i, bp in enumerate(enc.band_processors)], dim=1)      # :396-404
+        skip = enc.skip_maxpool(feats.transpose(1, 2)).transpose(1, 2)                                 # :407
+        y = enc.cross_band(feats) + enc.skip_weight * skip                                             # :411-415
+        y = enc.temporal_reduction(y)                                                                  # :419
+        logits = enc.to_simplices(y.flatten(1))                                                        # :423-426
+    names = sorted(k for k, _ in enc.named_parameters())
+    return {"seed": np.int64(seed), "n_vertices": np.int64(n), "logits": logits.numpy(), "bands_out": feats[:, :, :8].numpy(),
+            "param_names": np.array(names), "n_params": np.int64(sum(p.numel() for p in enc.parameters()))}
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     written = {}
+    written["ref_frontend"] = gen_frontend()
     written["ref_gumbel"] = gen_gumbel()
     for n in (6, 9):
         written[f"ref_glue_n{n}"] = gen_glue(n)

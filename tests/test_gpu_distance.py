@@ -43,3 +43,63 @@ def test_full_length_clips_and_row_sharding():
     shards = [prep.rows(*pd.shard_rows(70, r, 4)) for r in range(4)]
     assert torch.equal(torch.cat(shards), full)
     assert torch.equal(full, full.t())
+
+
+def test_streaming_topk_sweep_equals_the_dense_matrix():
+    """Config 5 machinery at a size the dense path can check: resident row blocks against column blocks prepared on the
+    fly (audio in pinned host memory), running top-k merge, row-sharded; nothing of size N x N is formed."""
+    from topo_audio_autoencoder_b200 import precompute_distances as pd
+    g = torch.Generator().manual_seed(9)
+    n, k = 37, 6
+    audio = torch.randn(n, 1, 6000, generator=g) * 0.1
+    dense = pd.pairwise_spectral_distances(audio.cuda())
+    want_v, want_i = pd.neighbour_order(dense)
+    for cache_bytes in (0, 48 << 30):             # columns re-prepared per row block / prepared once
+        vals, idx = pd.spectral_topk(audio.pin_memory(), k, row_block=16, col_block=8, cache_bytes=cache_bytes)
+        # the pair reduction is identical; the spectra come from cuFFT plans of different batch sizes (a block of clips
+        # instead of the whole collection), which differ in the last bits
+        assert_close("distance/topk-values", vals, want_v[:, :k], rtol=2e-6, atol=1e-6)
+        assert torch.equal(idx, want_i[:, :k])
+    shards = [pd.spectral_topk(audio.cuda(), k, row_block=5, col_block=16, rank=r, world_size=3) for r in range(3)]
+    assert_close("distance/topk-sharded", torch.cat([s[0] for s in shards]), want_v[:, :k], rtol=2e-6, atol=1e-6)
+    assert torch.equal(torch.cat([s[1] for s in shards]), want_i[:, :k])
+    # asymmetric normaliser across block borders: entry (i, j) and (j, i) of different blocks agree exactly
+    rows, cols = pd.prepare_block(audio[3:9], "cuda"), pd.prepare_block(audio[20:31], "cuda")
+    a, b = rows.block(cols, 3, 20), cols.block(rows, 20, 3)
+    assert torch.equal(a, b.t())
+    assert_close("distance/block-vs-dense", a, dense[3:9, 20:31], rtol=2e-6, atol=1e-6)
+    # the same prepared spectra through both entry points: bit-identical (tile position does not change a pair's arithmetic)
+    spec, seg = pd.multiscale_spectrograms(audio.cuda())
+    whole = pd.PreparedSpectra(spec, seg)
+    part_r, part_c = pd.PreparedSpectra(spec[3:9].contiguous(), seg), pd.PreparedSpectra(spec[20:31].contiguous(), seg)
+    assert torch.equal(part_r.block(part_c, 3, 20), whole.rows(3, 9, 20, 31))
+
+
+def test_compute_distances_top_k_files(tmp_path):
+    import pickle
+    import wave
+    import numpy as np
+    from topo_audio_autoencoder_b200 import precompute_distances as pd
+    g = torch.Generator().manual_seed(4)
+    adir, sdir = tmp_path / "a", tmp_path / "o"
+    adir.mkdir(); sdir.mkdir()
+    for j in range(9):
+        x = (torch.randn(5000 + 300 * j, generator=g) * 0.1).clamp(-1, 1)
+        with wave.open(str(adir / f"c{j}.wav"), "wb") as w:
+            w.setnchannels(1); w.setsampwidth(2); w.setframerate(16000)
+            w.writeframes(np.round(x.numpy() * 32767).astype(np.int16).tobytes())
+    dense = pd.compute_distances(adir, sdir)
+    with open(sdir / "neighbors.pkl", "rb") as f:
+        full = pickle.load(f)
+    res = pd.compute_distances(adir, sdir, top_k=3)
+    with open(sdir / "neighbors.pkl", "rb") as f:
+        top = pickle.load(f)
+    assert (sdir / "topk_distances.pt").exists() and tuple(res["indices"].shape) == (9, 3)
+    assert top["__file_to_idx__"] == full["__file_to_idx__"]
+    for name, rec in full.items():
+        if name == "__file_to_idx__":
+            continue
+        assert top[name]["sorted_neighbors"] == rec["sorted_neighbors"][:3]
+        assert top[name]["sorted_distances"] == rec["sorted_distances"][:3]
+        assert top[name]["index"] == rec["index"]
+    assert torch.equal(torch.load(sdir / "distance_matrix.pt"), dense)

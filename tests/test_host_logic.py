@@ -120,3 +120,115 @@ def test_tile_fragment_layout_is_a_permutation_of_each_tile():
             q, j0 = c // 2, (c % 2) * 2
             assert base == (row0 >> 7) * 2048 + (q * 4 + j0) * 128 + r
     assert (seen == 1).all()
+
+
+def _gather_topk_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from topo_audio_autoencoder_b200.precompute_distances import gather_topk, shard_rows
+    n, k = 7, 3
+    lo, hi = shard_rows(n, rank, world)
+    vals = torch.arange(lo, hi, dtype=torch.float32).unsqueeze(1) + torch.arange(k, dtype=torch.float32) * 0.1
+    idx = (torch.arange(lo, hi).unsqueeze(1) * 10 + torch.arange(k)).to(torch.int64)
+    gv, gi = gather_topk(vals, idx, n)
+    q.put((rank, gv.numpy().copy(), gi.numpy().copy()))
+    dist.destroy_process_group()
+
+
+def test_sharded_sweep_results_meet_in_one_gather():
+    """distance sweep, world size 2 over gloo: row shards of unequal size are padded, gathered once and trimmed"""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gather_topk_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want_v = torch.arange(7, dtype=torch.float32).unsqueeze(1) + torch.arange(3, dtype=torch.float32) * 0.1
+    want_i = (torch.arange(7).unsqueeze(1) * 10 + torch.arange(3)).to(torch.int64)
+    for _, gv, gi in got:
+        assert torch.equal(torch.from_numpy(gv), want_v) and torch.equal(torch.from_numpy(gi), want_i)
+
+
+class _TinyAutoencoder(torch.nn.Module):
+    """The interface Trainer needs (encoder with a sampler, decoder, forward -> (out, diversity, valid)) in pure torch."""
+
+    def __init__(self):
+        super().__init__()
+        self.encoder = torch.nn.Linear(4000, 8)
+        self.encoder.sampler = type("S", (), {"current_temp": 1.0})()
+        self.decoder = torch.nn.Linear(8, 4000)
+
+    def forward(self, bands, noise=None):
+        z = self.encoder(bands)
+        out = self.decoder(torch.tanh(z))
+        valid = torch.ones(bands.shape[0], dtype=torch.bool)
+        div = {"binary_entropy": z.mean(dim=(1, 2)), "diversity": z.pow(2).mean(dim=(1, 2))}
+        return out, div, valid
+
+
+def _trainer_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from topo_audio_autoencoder_b200.trainer import Trainer
+    torch.manual_seed(0)
+    tr = Trainer(_TinyAutoencoder(), device="cpu", accumulate_grad_batches=4)
+    assert tr.ddp is not None
+    g = torch.Generator().manual_seed(100)
+    data = torch.randn(2 * 4, 2, 2, 4000, generator=g) * 0.1            # [rank * micro, B, bands, T]
+    mine = [data[rank * 4 + i] for i in range(4)]
+    loss = tr.train_step(mine)
+    q.put((rank, loss.item(), {k: v.numpy().copy() for k, v in tr.model.state_dict().items()}, float(tr.last_grad_norm)))
+    dist.destroy_process_group()
+
+
+def test_data_parallel_training_step_accumulates_locally_and_reduces_once():
+    """trainer.py:271-293 on two gloo ranks: four micro-batches per rank, one gradient reduction, clipping after it.
+    Both replicas end with identical parameters, equal to a single process that saw all eight micro-batches."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() + 7) % 2000
+    procs = [ctx.Process(target=_trainer_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = sorted([q.get(timeout=180) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (_, _, sd0, n0), (_, _, sd1, n1) = got
+    assert abs(n0 - n1) < 1e-6 * max(n0, 1.0), "clipping must see the reduced gradients on every rank"
+    sd0 = {k: torch.from_numpy(v) for k, v in sd0.items()}
+    sd1 = {k: torch.from_numpy(v) for k, v in sd1.items()}
+    for k in sd0:
+        assert torch.equal(sd0[k], sd1[k]), f"replicas diverged at {k}"
+    # single-process reference: the mean over ranks of the per-rank accumulated gradient
+    from topo_audio_autoencoder_b200.trainer import Trainer
+    torch.manual_seed(0)
+    tr = Trainer(_TinyAutoencoder(), device="cpu", accumulate_grad_batches=4)
+    g = torch.Generator().manual_seed(100)
+    data = torch.randn(2 * 4, 2, 2, 4000, generator=g) * 0.1
+    for rank in range(2):
+        for i in range(4):
+            (tr.micro_batch_loss(data[rank * 4 + i]) / 2).backward()
+    torch.nn.utils.clip_grad_norm_(tr.model.parameters(), tr.gradient_clip_val)
+    tr.optimizer.step()
+    for k, v in tr.model.state_dict().items():
+        assert torch.allclose(v, sd0[k], rtol=1e-5, atol=1e-6), k
+
+
+def test_checkpoint_dictionary_has_the_reference_schema(tmp_path):
+    from topo_audio_autoencoder_b200.trainer import Trainer
+    tr = Trainer(_TinyAutoencoder(), checkpoint_dir=str(tmp_path), device="cpu")
+    assert [g["lr"] for g in tr.optimizer.param_groups] == [1e-3, 1e-4]            # trainer.py:84-87
+    tr.train_step([torch.randn(2, 2, 4000) * 0.1 for _ in range(4)])
+    path = tr.save_checkpoint("epoch_0_iter_0")
+    ck = torch.load(path, weights_only=False)
+    assert sorted(ck) == ["hyperparameters", "metrics", "model_state_dict", "optimizer_state_dict"]      # :421-431
+    assert sorted(ck["hyperparameters"]) == ["complexity_penalty", "decoder_lr", "encoder_lr"]
+    tr.optimizer.param_groups[0]["lr"] = 5.0
+    tr.load_checkpoint("epoch_0_iter_0")
+    assert tr.optimizer.param_groups[0]["lr"] == 1e-3
+    assert tr.set_epoch(3) == max(0.1, 5.0 * 0.95 ** 3) and tr.model.encoder.sampler.current_temp == tr.set_epoch(3)

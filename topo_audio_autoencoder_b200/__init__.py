@@ -10,9 +10,16 @@ from .complex_builder import SparseSimplicialMatrices, build_sparse_matrices    
 from .gate import HardConcrete, BinaryGumbel, hard_concrete                         # noqa: F401
 from .custom_sccn import GradientSCCN, GradientSCCNLayer, BatchedComplex, Conv      # noqa: F401
 from .encoder_complex import ComplexHead, ComplexStage, active_sets                 # noqa: F401
+from .decoder import AudioDecoder, DecoderTail                                      # noqa: F401
+from .frontend import ConvFrontEnd                                                  # noqa: F401
+from .audio2complex import AudioAutoencoder, AudioEncoder                           # noqa: F401
+from .loss import AutoencoderLoss, spectral_distance                                # noqa: F401
+from .trainer import Trainer                                                        # noqa: F401
 
 __all__ = [
     "ConstraintMatrices", "SimplexIndices", "RectifiedProbs", "enforce_constraints", "rectify_batch",
     "SparseSimplicialMatrices", "build_sparse_matrices", "HardConcrete", "BinaryGumbel", "hard_concrete",
     "GradientSCCN", "GradientSCCNLayer", "BatchedComplex", "Conv", "ComplexHead", "ComplexStage", "active_sets",
+    "AudioDecoder", "DecoderTail", "ConvFrontEnd", "AudioAutoencoder", "AudioEncoder", "AutoencoderLoss",
+    "spectral_distance", "Trainer",
 ]

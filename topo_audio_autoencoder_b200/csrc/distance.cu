@@ -88,12 +88,21 @@ struct Stage {
 };
 
 // 256 threads: ty = tid / 16 owns rows ty*4..+3, tx = tid % 16 owns columns tx*4..+3
-__global__ void __launch_bounds__(256) distance_rows_kernel(const float* __restrict__ spec_p,
-                                                               const float* __restrict__ logspec_p,
-                                                               const float* __restrict__ sq_mean, long long n,
-                                                               Segments seg, long long row_begin, long long row_end,
+// Rows and columns may come from DIFFERENT prepared blocks (streaming sweep: a resident row block against column blocks
+// prepared on the fly): `rows` holds clips [row_g0, row_g0 + n_rows) of the collection, `cols` clips [col_g0, col_g0 +
+// n_cols); the kernel reduces rows [row_begin, row_end) x columns [col_begin, col_end) given as LOCAL indices.
+struct DistOperand {
+    const float* spec;      // [count, dp] padded spectrogram rows
+    const float* logspec;   // [count, dp] log(x + eps)
+    const float* sq_mean;   // [count, n_scales]
+    long long count;        // clips in this block
+    long long g0;           // index of its first clip in the whole collection
+};
+
+__global__ void __launch_bounds__(256) distance_rows_kernel(DistOperand rows, DistOperand cols, Segments seg,
+                                                               long long row_begin, long long row_end,
                                                                long long col_begin, long long col_end,
-                                                               float* __restrict__ out) {
+                                                               float* __restrict__ out, long long ld_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Stage* st = reinterpret_cast<Stage*>(smem_raw);   // [2]
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -102,12 +111,12 @@ __global__ void __launch_bounds__(256) distance_rows_kernel(const float* __restr
 
     // loader role: 4 threads per row fetch 16 consecutive bins (one float4 each) of that row
     const int l_row = tid >> 2, l_k = (tid & 3) * 4;
-    const long long gi = min(i0 + l_row, n - 1);
-    const long long gj = min(j0 + l_row, n - 1);
-    const float* px = spec_p + gi * seg.dp + l_k;
-    const float* plx = logspec_p + gi * seg.dp + l_k;
-    const float* py = spec_p + gj * seg.dp + l_k;
-    const float* ply = logspec_p + gj * seg.dp + l_k;
+    const long long gi = min(i0 + l_row, rows.count - 1);
+    const long long gj = min(j0 + l_row, cols.count - 1);
+    const float* px = rows.spec + gi * seg.dp + l_k;
+    const float* plx = rows.logspec + gi * seg.dp + l_k;
+    const float* py = cols.spec + gj * seg.dp + l_k;
+    const float* ply = cols.logspec + gj * seg.dp + l_k;
 
     float4 r[4];
     auto fetch = [&](long long k0) {
@@ -184,21 +193,20 @@ __global__ void __launch_bounds__(256) distance_rows_kernel(const float* __restr
             if (more) deposit(st[(g + 1) & 1]);
             __syncthreads();
         }
-        // fold this scale: the normaliser belongs to the lower-index clip of the pair
+        // fold this scale: the normaliser belongs to the lower-index clip of the pair (collection-wide indices)
         const float inv_len = 1.0f / static_cast<float>(seg.len[s]);
 #pragma unroll
         for (int a = 0; a < 4; ++a) {
-            const long long i = i0 + ty * 4 + a;
+            const long long i = min(i0 + ty * 4 + a, rows.count - 1);
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-                const long long j = j0 + tx * 4 + c;
-                const long long lo = min(min(i, j), n - 1);
-                const float norm = __ldg(sq_mean + lo * seg.n + s) + 1e-7f;
+                const long long j = min(j0 + tx * 4 + c, cols.count - 1);
+                const bool row_is_lower = rows.g0 + i <= cols.g0 + j;
+                const float norm = (row_is_lower ? __ldg(rows.sq_mean + i * seg.n + s) : __ldg(cols.sq_mean + j * seg.n + s)) + 1e-7f;
                 dist[a][c] += (sq[a][c] * inv_len) / norm + l1[a][c] * inv_len;
             }
         }
     }
-    const long long n_cols = col_end - col_begin;
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
         const long long i = i0 + ty * 4 + a;
@@ -206,7 +214,7 @@ __global__ void __launch_bounds__(256) distance_rows_kernel(const float* __restr
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
             const long long j = j0 + tx * 4 + c;
-            if (j < col_end) out[(i - row_begin) * n_cols + (j - col_begin)] = (i == j) ? 0.f : dist[a][c];
+            if (j < col_end) out[(i - row_begin) * ld_out + (j - col_begin)] = (rows.g0 + i == cols.g0 + j) ? 0.f : dist[a][c];
         }
     }
 }
@@ -241,6 +249,17 @@ extern "C" int topo_distance_prepare(const float* spec, int64_t n, int64_t d, co
     return TOPO_OK;
 }
 
+static int launch_distance(const DistOperand& rows, const DistOperand& cols, const Segments& seg, int64_t row_begin,
+                           int64_t row_end, int64_t col_begin, int64_t col_end, float* out, int64_t ld_out, topo_stream_t stream) {
+    const dim3 grid(static_cast<unsigned>((col_end - col_begin + TJ - 1) / TJ),
+                    static_cast<unsigned>((row_end - row_begin + TI - 1) / TI));
+    if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(distance_rows_kernel), 2 * sizeof(Stage))) return rc;
+    distance_rows_kernel<<<grid, 256, 2 * sizeof(Stage), as_stream(stream)>>>(rows, cols, seg, row_begin, row_end, col_begin,
+                                                                               col_end, out, ld_out);
+    TOPO_LAUNCH_CHECK();
+    return TOPO_OK;
+}
+
 extern "C" int topo_distance_rows(const float* spec_p, const float* logspec_p, const float* sq_mean, int64_t n,
                                   const int64_t* seg_len, int n_scales, int64_t row_begin, int64_t row_end,
                                   int64_t col_begin, int64_t col_end, float* out, topo_stream_t stream) {
@@ -250,11 +269,20 @@ extern "C" int topo_distance_rows(const float* spec_p, const float* logspec_p, c
     TOPO_REQUIRE(0 <= col_begin && col_begin <= col_end && col_end <= n, "bad column range");
     if (row_begin == row_end || col_begin == col_end) return TOPO_OK;
     const Segments seg = make_segments(seg_len, n_scales);
-    const dim3 grid(static_cast<unsigned>((col_end - col_begin + TJ - 1) / TJ),
-                    static_cast<unsigned>((row_end - row_begin + TI - 1) / TI));
-    if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(distance_rows_kernel), 2 * sizeof(Stage))) return rc;
-    distance_rows_kernel<<<grid, 256, 2 * sizeof(Stage), as_stream(stream)>>>(
-        spec_p, logspec_p, sq_mean, n, seg, row_begin, row_end, col_begin, col_end, out);
-    TOPO_LAUNCH_CHECK();
-    return TOPO_OK;
+    const DistOperand all{spec_p, logspec_p, sq_mean, n, 0};
+    return launch_distance(all, all, seg, row_begin, row_end, col_begin, col_end, out, col_end - col_begin, stream);
+}
+
+extern "C" int topo_distance_block(const float* row_spec, const float* row_logspec, const float* row_sq_mean, int64_t n_rows,
+                                   int64_t row_global0, const float* col_spec, const float* col_logspec,
+                                   const float* col_sq_mean, int64_t n_cols, int64_t col_global0, const int64_t* seg_len,
+                                   int n_scales, float* out, int64_t ld_out, topo_stream_t stream) {
+    TOPO_REQUIRE(row_spec && row_logspec && row_sq_mean && col_spec && col_logspec && col_sq_mean && seg_len && out, "null argument");
+    TOPO_REQUIRE(n_scales >= 1 && n_scales <= kMaxScales, "n_scales must be in [1, 8]");
+    TOPO_REQUIRE(n_rows >= 0 && n_cols >= 0 && row_global0 >= 0 && col_global0 >= 0 && ld_out >= n_cols, "bad block geometry");
+    if (n_rows == 0 || n_cols == 0) return TOPO_OK;
+    const Segments seg = make_segments(seg_len, n_scales);
+    const DistOperand rows{row_spec, row_logspec, row_sq_mean, n_rows, row_global0};
+    const DistOperand cols{col_spec, col_logspec, col_sq_mean, n_cols, col_global0};
+    return launch_distance(rows, cols, seg, 0, n_rows, 0, n_cols, out, ld_out, stream);
 }

@@ -18,11 +18,19 @@ import torch.nn.functional as F
 from ._lib import lib, check, ptr, stream, i64_array
 
 
+def _aligned(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    """The gate kernels move 128 bits per access: a row sliced out of a [B, N] batch with N % 4 != 0 starts at an address
+    that is not 16-byte aligned and is copied once."""
+    if t is None:
+        return None
+    t = t.contiguous()
+    return t if t.data_ptr() % 16 == 0 else t.clone()
+
+
 class _HardConcreteFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, logits, u, params, offsets, training, ste):
-        logits = logits.contiguous()
-        u = u.contiguous() if u is not None else None
+        logits, u = _aligned(logits), _aligned(u)
         params = params.contiguous()
         z = torch.empty_like(logits)
         batch = logits.numel() // offsets[4]
@@ -36,7 +44,7 @@ class _HardConcreteFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_z):
         logits, u, params = ctx.saved_tensors
-        grad_z = grad_z.contiguous()
+        grad_z = _aligned(grad_z)
         grad_logits = torch.empty_like(logits)
         grad_params = torch.empty(7, dtype=torch.float32, device=logits.device)
         check(lib.topo_hard_concrete_bwd(ptr(logits), ptr(u), ptr(params), i64_array(ctx.offsets), ctx.batch,
@@ -108,7 +116,7 @@ class HardConcrete(nn.Module):
 class _BinaryGumbelFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, logits, gumbels, temp):
-        logits, gumbels = logits.contiguous(), gumbels.contiguous()
+        logits, gumbels = _aligned(logits), _aligned(gumbels)
         probs = torch.empty_like(logits)
         check(lib.topo_binary_gumbel_fwd(ptr(logits), ptr(gumbels), float(temp), logits.numel(), ptr(probs), stream()))
         ctx.save_for_backward(logits, gumbels)
@@ -119,7 +127,7 @@ class _BinaryGumbelFn(torch.autograd.Function):
     def backward(ctx, grad_probs):
         logits, gumbels = ctx.saved_tensors
         grad = torch.empty_like(logits)
-        grad_probs = grad_probs.contiguous()
+        grad_probs = _aligned(grad_probs)
         check(lib.topo_binary_gumbel_bwd(ptr(logits), ptr(gumbels), ctx.temp, logits.numel(),
                                          ptr(grad_probs), ptr(grad), stream()))
         return grad, None, None

@@ -72,6 +72,24 @@ class PreparedSpectra:
         check(lib.topo_distance_prepare(ptr(spec), self.n, self.d, self.seg_c, len(self.seg_len), float(log_eps),
                                         ptr(self.spec_p), ptr(self.logspec_p), ptr(self.sq_mean), stream()))
 
+    def block(self, cols: "PreparedSpectra", row_global0: int = 0, col_global0: int = 0,
+              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """All pairs (row clip of self, column clip of `cols`) -> [self.n, cols.n].  The two blocks are slices
+        [row_global0, ...) and [col_global0, ...) of one collection: the collection-wide indices decide which clip of a
+        pair supplies the normaliser (the lower one, reference :89, :106-110) and where the zero diagonal is."""
+        if cols.seg_len != self.seg_len:
+            raise ValueError("row and column blocks were prepared with different scale segments")
+        if out is None:
+            out = torch.empty(self.n, cols.n, dtype=torch.float32, device=self.spec_p.device)
+        # `out` may be a column window of a wider buffer (the running top-k merge): unit column stride, any row stride
+        if not (out.is_cuda and out.dtype == torch.float32 and out.dim() == 2 and out.stride(1) == 1
+                and out.shape[0] >= self.n and out.shape[1] >= cols.n):
+            raise ValueError("out must be a CUDA float32 [rows, >= columns] view with unit column stride")
+        check(lib.topo_distance_block(ptr(self.spec_p), ptr(self.logspec_p), ptr(self.sq_mean), self.n, int(row_global0),
+                                      ptr(cols.spec_p), ptr(cols.logspec_p), ptr(cols.sq_mean), cols.n, int(col_global0),
+                                      self.seg_c, len(self.seg_len), out.data_ptr(), out.stride(0), stream()))
+        return out
+
     def rows(self, row_begin: int, row_end: int, col_begin: int = 0, col_end: Optional[int] = None) -> torch.Tensor:
         col_end = self.n if col_end is None else col_end
         out = torch.empty(row_end - row_begin, col_end - col_begin, dtype=torch.float32, device=self.spec_p.device)
@@ -92,6 +110,88 @@ def pairwise_spectral_distances(audio: torch.Tensor, scales: Sequence[int] = SCA
 def shard_rows(n: int, rank: int, world_size: int):
     per = (n + world_size - 1) // world_size
     return min(rank * per, n), min((rank + 1) * per, n)
+
+
+def prepare_block(audio_block: torch.Tensor, device, scales: Sequence[int] = SCALES) -> PreparedSpectra:
+    """Front half for one block of clips (host or device tensor [n, 1, T] / [n, T]): H2D copy if needed, multi-scale
+    STFT (cuFFT through torch.stft -- a library call), padded spectra + logs + mean squares (csrc/distance.cu)."""
+    x = audio_block.to(device, non_blocking=True)
+    spec, seg = multiscale_spectrograms(x, scales)
+    return PreparedSpectra(spec, seg)
+
+
+@torch.no_grad()
+def spectral_topk(audio: torch.Tensor, k: int, row_block: int = 1024, col_block: int = 2048, rank: int = 0,
+                  world_size: int = 1, device=None, scales: Sequence[int] = SCALES, cache_bytes: int = 48 << 30):
+    """Streaming sweep for collections whose spectra do not fit in HBM (config 5: 100k clips x 2.58 MB x 2 arrays).
+
+    The rows owned by `rank` (contiguous row blocks, no collective on the compute path) are processed `row_block` clips
+    at a time: their spectra stay resident while every `col_block` of the collection is prepared on the fly from the
+    audio -- which may live in (pinned) host memory -- and reduced against them; only the k nearest neighbours of each
+    row survive a block (running top-k merge), so nothing of size N x N is ever formed.  When all column spectra fit in
+    `cache_bytes` they are prepared once instead.
+
+    Launch geometry: one launch reduces row_block x col_block pairs in 64 x 64 tiles, so the blocks are chosen large
+    enough for several CTAs per SM (1024 x 2048 = 512 tiles on 148 SMs); a row block of 1024 clips keeps 5.3 GB resident.
+
+    -> (distances [rows, k] ascending, neighbour indices [rows, k] int64, collection-wide; self excluded,
+        reference :121-126), on `device`."""
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    n = audio.shape[0]
+    k = min(int(k), max(n - 1, 0))
+    lo, hi = shard_rows(n, rank, world_size)
+    vals = torch.empty(hi - lo, k, dtype=torch.float32, device=device)
+    idx = torch.empty(hi - lo, k, dtype=torch.int64, device=device)
+    if hi == lo or k == 0:
+        return vals, idx
+    col_starts = list(range(0, n, col_block))
+    probe = prepare_block(audio[:1], device, scales)
+    per_clip = 2 * probe.dp * 4
+    cached = None
+    if n * per_clip <= cache_bytes:
+        cached = [prepare_block(audio[c0:c0 + col_block], device, scales) for c0 in col_starts]
+    scratch = torch.empty(min(row_block, hi - lo), k + col_block, dtype=torch.float32, device=device)
+    scratch_i = torch.empty(min(row_block, hi - lo), k + col_block, dtype=torch.int64, device=device)
+    for r0 in range(lo, hi, row_block):
+        r1 = min(r0 + row_block, hi)
+        rows = prepare_block(audio[r0:r1], device, scales)
+        m = r1 - r0
+        best_v = scratch[:m, :k].fill_(float("inf"))
+        best_i = scratch_i[:m, :k].fill_(-1)
+        row_ids = torch.arange(r0, r1, device=device).unsqueeze(1)
+        for ci, c0 in enumerate(col_starts):
+            cols = cached[ci] if cached is not None else prepare_block(audio[c0:c0 + col_block], device, scales)
+            width = cols.n
+            d = scratch[:m, k:k + width]
+            rows.block(cols, r0, c0, out=d)
+            col_ids = torch.arange(c0, c0 + width, device=device).unsqueeze(0)
+            d.masked_fill_(row_ids == col_ids, float("inf"))                     # drop self (reference :124-126)
+            scratch_i[:m, k:k + width] = col_ids
+            v, sel = torch.topk(scratch[:m, :k + width], k, dim=1, largest=False, sorted=True)
+            i_sel = torch.gather(scratch_i[:m, :k + width], 1, sel)
+            best_v.copy_(v)
+            best_i.copy_(i_sel)
+        vals[r0 - lo:r1 - lo] = best_v
+        idx[r0 - lo:r1 - lo] = best_i
+    return vals, idx
+
+
+def gather_topk(vals: torch.Tensor, idx: torch.Tensor, n: int):
+    """The ONE exchange of the sharded sweep: every rank's [rows, k] results -> [n, k] on every rank (NCCL all-gather of
+    equally padded shards; a no-op without an initialised process group)."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return vals, idx
+    world = dist.get_world_size()
+    per = (n + world - 1) // world
+    pv = torch.full((per, vals.shape[1]), float("inf"), dtype=vals.dtype, device=vals.device)
+    pi = torch.full((per, idx.shape[1]), -1, dtype=idx.dtype, device=idx.device)
+    pv[:vals.shape[0]], pi[:idx.shape[0]] = vals, idx
+    gv = torch.empty(world * per, vals.shape[1], dtype=vals.dtype, device=vals.device)
+    gi = torch.empty(world * per, idx.shape[1], dtype=idx.dtype, device=idx.device)
+    dist.all_gather_into_tensor(gv, pv)
+    dist.all_gather_into_tensor(gi, pi)
+    return gv[:n], gi[:n]
 
 
 class BatchAudioDistance(nn.Module):
@@ -140,21 +240,43 @@ def neighbour_order(distances: torch.Tensor):
     return vals[:, 1:], idx[:, 1:]
 
 
-def compute_distances(audio_dir: Path, save_path: Path, batch_size: int = 32):
-    """reference :51-153.  Same inputs and the same two output files (distance_matrix.pt,
-    neighbors.pkl with 'sorted_neighbors' / 'sorted_distances' / 'index' per file and the
-    '__file_to_idx__' map); ``batch_size`` is accepted for signature parity and unused."""
-    audio_files = list(Path(audio_dir).glob("*.wav"))
-    n_files = len(audio_files)
-    file_to_idx = {str(f): i for i, f in enumerate(audio_files)}
+def _load_padded(audio_files) -> torch.Tensor:
+    """reference :72-85: load every file, zero-pad to the longest, stack -> [N, 1, T] (host)."""
     wavs, max_len = [], 0
     for f in audio_files:
         wav = load_wav(f)
         wavs.append(wav.unsqueeze(0))
         max_len = max(max_len, wav.shape[-1])
-    audio = torch.cat([torch.nn.functional.pad(w, (0, max_len - w.shape[2])) for w in wavs], dim=0).cuda()
-    distances = pairwise_spectral_distances(audio[:, :1]).cpu()
-    sorted_vals, sorted_idx = neighbour_order(distances)
+    return torch.cat([torch.nn.functional.pad(w, (0, max_len - w.shape[2])) for w in wavs], dim=0)[:, :1]
+
+
+def compute_distances(audio_dir: Path, save_path: Path, batch_size: int = 32, top_k: Optional[int] = None,
+                      rank: int = 0, world_size: int = 1):
+    """reference :51-153.  Same inputs and, by default, the same two output files (distance_matrix.pt: dense [N, N]
+    fp32; neighbors.pkl: per file 'sorted_neighbors' / 'sorted_distances' / 'index', plus the '__file_to_idx__' map);
+    ``batch_size`` is accepted for signature parity and unused.
+
+    ``top_k`` (this repo's addition for collections where a dense matrix and fully sorted rows are impractical -- 40 GB
+    and 10^10 list entries at 100k clips): the streaming sweep of ``spectral_topk`` instead; neighbors.pkl then holds the
+    k nearest neighbours per file in the same schema and distance_matrix.pt is replaced by topk_distances.pt
+    ({'distances': [N, k], 'indices': [N, k]}).  With ``world_size`` > 1 every rank sweeps its row block and the results
+    meet in one all-gather; rank 0 writes the files."""
+    audio_files = list(Path(audio_dir).glob("*.wav"))
+    n_files = len(audio_files)
+    file_to_idx = {str(f): i for i, f in enumerate(audio_files)}
+    audio = _load_padded(audio_files)
+    save_path = Path(save_path)
+    if top_k is None:
+        distances = pairwise_spectral_distances(audio.cuda()).cpu()
+        sorted_vals, sorted_idx = neighbour_order(distances)
+        result = distances
+    else:
+        vals, idx = spectral_topk(audio.pin_memory() if audio.numel() else audio, top_k, rank=rank, world_size=world_size)
+        vals, idx = gather_topk(vals, idx, n_files)
+        sorted_vals, sorted_idx = vals.cpu(), idx.cpu()
+        result = {"distances": sorted_vals, "indices": sorted_idx}
+    if rank != 0:
+        return result
     neighbors = {
         str(audio_files[i]): {
             "sorted_neighbors": [str(audio_files[j]) for j in sorted_idx[i].tolist()],
@@ -163,8 +285,7 @@ def compute_distances(audio_dir: Path, save_path: Path, batch_size: int = 32):
         } for i in range(n_files)
     }
     neighbors["__file_to_idx__"] = file_to_idx
-    save_path = Path(save_path)
-    torch.save(distances, save_path / "distance_matrix.pt")
+    torch.save(result, save_path / ("distance_matrix.pt" if top_k is None else "topk_distances.pt"))
     with open(save_path / "neighbors.pkl", "wb") as f:
         pickle.dump(neighbors, f)
-    return distances
+    return result
