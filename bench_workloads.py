@@ -274,10 +274,12 @@ def run_full_step(args):
     per_step = world * B * M
     value, e2e_value = per_step * args.steps / (ms * 1e-3), per_step * args.steps / (ms_e2e * 1e-3)
     breakdown = None
-    if rank == 0 and not args.no_profile_pass:
+    if not args.no_profile_pass:
+        # every rank takes this extra step (its last backward is a collective); rank 0 alone reports
         T.lib.start_timing()
         step(False)
         stats = T.lib.stop_timing()
+    if rank == 0 and not args.no_profile_pass:
         lib_ms = sum(v[1] for v in stats.values())
         breakdown = {"libtopo_b200_kernels_ms_per_step": lib_ms, "share_of_step": lib_ms / (ms / args.steps),
                      "note": "the rest is the stock PyTorch front-end, decoder tail, loss (cuFFT), optimizer and the all-reduce"}
