@@ -16,6 +16,7 @@ cores, a bounded number of clips per step.
 from __future__ import annotations
 
 import argparse
+import datetime
 import json
 import os
 import statistics
@@ -35,6 +36,18 @@ METRIC = "complex_stage_fwd_bwd_samples_per_sec"
 UNIT = "samples/s"
 # SURVEY.md 8(d) / BASELINE.md 5: algorithmic HBM bytes per sample, default full complex, fwd+bwd
 SURVEY_BYTES_PER_SAMPLE_FULL = 121.2e6
+
+
+def survey_bytes_per_sample(n, channels, layers):
+    """SURVEY.md 8(d), full complex on n vertices: gate 24 N + rectifier 16 N + operator values 8 (nnzA + nnzI) + SCCN
+    L x 3 x (2 F + 8 (nnzA + 2 nnzI)), F = 4 C N (backward counted as twice the forward).  n = 20, C = 64, L = 6: 121.27 MB."""
+    from math import comb
+    cnt = [comb(n, k) for k in (1, 2, 3, 4)]
+    total = sum(cnt)
+    nnz_a = n * (n - 1) + 2 * (n - 2) * cnt[1] + 3 * (n - 3) * cnt[2] + 4 * (n - 4) * cnt[3]
+    nnz_i = 2 * cnt[1] + 3 * cnt[2] + 4 * cnt[3]
+    feat = 4 * channels * total
+    return float(24 * total + 16 * total + 8 * (nnz_a + nnz_i) + layers * 3 * (2 * feat + 8 * (nnz_a + 2 * nnz_i)))
 
 
 def parse_args():
@@ -166,9 +179,11 @@ def run_reference(args):
 
 
 def workload_config(args, batch):
-    return {"workload": f"complex stage fwd+bwd: {args.vertices} vertices (6195 candidate simplices), C={args.channels}, "
+    from math import comb
+    n_simplices = sum(comb(args.vertices, k) for k in (1, 2, 3, 4))
+    return {"workload": f"complex stage fwd+bwd: {args.vertices} vertices ({n_simplices} candidate simplices), C={args.channels}, "
                         f"{args.layers} SCCN layers, regime={args.regime}",
-            "clips_per_gpu_per_step": batch, "clip": "4 s @ 16 kHz NSynth-shaped (enters the stage as a [6195] logit vector)",
+            "clips_per_gpu_per_step": batch, "clip": f"4 s @ 16 kHz NSynth-shaped (enters the stage as a [{n_simplices}] logit vector)",
             "gate": "BinaryGumbel (shipped, encoder.py:26-53)" if args.regime == "full" else "HardConcrete (builder's spec)",
             "parallelism": f"dp{args.gpus} (batch-sharded, gradient all-reduce)"}
 
@@ -270,7 +285,7 @@ def run_ours(args):
         raise SystemExit("bench.py --impl ours needs a CUDA device: there is no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=180))
     dev = torch.device("cuda", local)
 
     torch.manual_seed(SEED)     # identical replicas on every rank
@@ -428,7 +443,7 @@ def run_ours(args):
                 roofline["frac_on_survey_budget"] = sv["backward"]["frac"]
                 roofline["note"] = ("frac = the kernel's own compulsory traffic (it re-reads saved activations and aggregates) / time; "
                                     "frac_on_survey_budget = SURVEY 8(d) bytes of the whole SCCN backward / (combine + aggregation time)")
-    stage_bytes = SURVEY_BYTES_PER_SAMPLE_FULL if args.regime == "full" and args.vertices == 20 and args.layers == 6 else None
+    stage_bytes = survey_bytes_per_sample(args.vertices, args.channels, args.layers) if args.regime == "full" else None
     roofline_stage = None
     if stage_bytes:
         ach = stage_bytes * value / world / 1e9

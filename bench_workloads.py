@@ -7,6 +7,7 @@
 """
 from __future__ import annotations
 
+import datetime
 import json
 import os
 import time
@@ -53,7 +54,7 @@ def run_distance(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     n, R, k = args.clips, args.row_block, args.top_k
     audio_h = _clips(n, args.clip_samples, SEED).pin_memory()       # identical collection on every rank
     # column spectra: prepared once when they fit (pd.spectral_topk does the same), in blocks of 512 clips
@@ -225,7 +226,7 @@ def run_full_step(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     torch.manual_seed(SEED)
     kw = dict(gate="binary_gumbel", bias_on="probs") if args.regime == "full" else dict(gate="hard_concrete", bias_on="logits")
     model = T.AudioAutoencoder(num_vertices=args.vertices, sccn_hidden_dim=args.channels, **kw)
