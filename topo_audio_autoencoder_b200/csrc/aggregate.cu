@@ -180,8 +180,10 @@ __device__ __forceinline__ void gather4(const Group<L, V>& g, const float* base,
 // kernel (the shuffles are warp-wide) with valid == false and id == 0.
 // kDense: test whether whole ranks are active and skip the position / id lookups for them (forward kernels; the
 // backward kernels run at 32 registers and have none to spare for the flag).
+// Returns false when not a single group of this block owns a live row (a sparse complex: the chunk lies past the
+// sample's active count); the whole block then leaves at once -- nothing it could compute is ever stored.
 template <int L, int V, bool kDense>
-__device__ __forceinline__ void locate(const DeviceTables& d, const Sections& sec, const topo_complex_view& cv,
+__device__ __forceinline__ bool locate(const DeviceTables& d, const Sections& sec, const topo_complex_view& cv,
                                        Group<L, V>* g, int* rank, int* row, int* id, long long* axis, int first_block = 0) {
     constexpr int kGroups = kThreads / L;
     const int blk = blockIdx.x + first_block;          // a launch may cover a suffix of the sections (one rank)
@@ -201,13 +203,17 @@ __device__ __forceinline__ void locate(const DeviceTables& d, const Sections& se
     g->lane = threadIdx.x % L;
     g->mask = 0xffffffffu;
     g->dense = 0u;
+    int live_r;
     if constexpr (kDense) {
         const int4 cnt = __ldg(reinterpret_cast<const int4*>(cv.counts) + b);
         g->dense = (cnt.x == d.cnt[0] ? 1u : 0u) | (cnt.y == d.cnt[1] ? 2u : 0u) | (cnt.z == d.cnt[2] ? 4u : 0u) | (cnt.w == d.cnt[3] ? 8u : 0u);
-        g->valid = i < (r == 0 ? cnt.x : (r == 1 ? cnt.y : (r == 2 ? cnt.z : cnt.w)));
+        live_r = r == 0 ? cnt.x : (r == 1 ? cnt.y : (r == 2 ? cnt.z : cnt.w));
     } else {
-        g->valid = i < cv.counts[b * 4 + r];
+        live_r = cv.counts[b * 4 + r];
     }
+    g->valid = i < live_r;
+    // block-uniform: the first row of this chunk against the sample's live count of the rank
+    const int chunk_first = (rel - b * chunks) * kGroups;
     const int B1 = static_cast<int>(cv.batch) + 1;
 #pragma unroll
     for (int q = 0; q < 4; ++q) g->ro[q] = cv.row_off[q * B1 + b];
@@ -216,6 +222,7 @@ __device__ __forceinline__ void locate(const DeviceTables& d, const Sections& se
     *row = ro_r + (g->valid ? i : 0);
     *id = g->valid ? ((g->dense & (1u << r)) ? i : cv.act_idx[ax + off_r + i]) : 0;
     *axis = ax;
+    return chunk_first < live_r;
 }
 
 // ------------------------------------------------------------------ forward, phase 1: cross-rank
@@ -259,7 +266,7 @@ __global__ void __launch_bounds__(kThreads) agg_cross_fwd(const DeviceTables d, 
     Group<L, V> g;
     int r, row, id;
     long long axis;
-    locate<L, V, true>(d, sec, cv, &g, &r, &row, &id, &axis);
+    if (!locate<L, V, true>(d, sec, cv, &g, &r, &row, &id, &axis)) return;
     switch (r) {
         case 0: cross_fwd_body<L, V, 0>(d, g, row, id, x, down, up); break;
         case 1: cross_fwd_body<L, V, 1>(d, g, row, id, x, down, up); break;
@@ -355,7 +362,7 @@ __global__ void __launch_bounds__(kThreads) agg_same_fwd(const DeviceTables d, c
     Group<L, V> g;
     int r, row, id;
     long long axis;
-    locate<L, V, true>(d, sec, cv, &g, &r, &row, &id, &axis);
+    if (!locate<L, V, true>(d, sec, cv, &g, &r, &row, &id, &axis)) return;
     switch (r) {
         case 0: same_fwd_body<L, V, 0>(d, g, row, id, x, down, up, same); break;
         case 1: same_fwd_body<L, V, 1>(d, g, row, id, x, down, up, same); break;
@@ -486,7 +493,7 @@ __global__ void __launch_bounds__(kThreads, V == 1 ? 8 : 5) agg_same_bwd(const D
     Group<L, V> g;
     int r, row, id;
     long long axis;
-    locate<L, V, false>(d, sec, cv, &g, &r, &row, &id, &axis);
+    if (!locate<L, V, false>(d, sec, cv, &g, &r, &row, &id, &axis)) return;
     switch (r) {
         case 0: same_bwd_body<L, V, 0>(d, g, row, id, axis, x, down, up, g_same, g_down, g_up, g_x, g_probs); break;
         case 1: same_bwd_body<L, V, 1>(d, g, row, id, axis, x, down, up, g_same, g_down, g_up, g_x, g_probs); break;
@@ -555,7 +562,7 @@ __global__ void __launch_bounds__(kThreads) agg_cross_bwd(const DeviceTables d, 
     Group<L, V> g;
     int r, row, id;
     long long axis;
-    locate<L, V, false>(d, sec, cv, &g, &r, &row, &id, &axis);
+    if (!locate<L, V, false>(d, sec, cv, &g, &r, &row, &id, &axis)) return;
     switch (r) {
         case 0: cross_bwd_body<L, V, 0>(d, g, row, id, axis, x, g_down, g_up, g_x, g_probs); break;
         case 1: cross_bwd_body<L, V, 1>(d, g, row, id, axis, x, g_down, g_up, g_x, g_probs); break;
@@ -578,7 +585,7 @@ __global__ void __launch_bounds__(kThreads, 4) agg_top_bwd(const DeviceTables d,
     Group<L, V> g;
     int r, row, id;
     long long axis;
-    locate<L, V, false>(d, sec, cv, &g, &r, &row, &id, &axis, sec.begin[3]);
+    if (!locate<L, V, false>(d, sec, cv, &g, &r, &row, &id, &axis, sec.begin[3])) return;
     using F = FV<V>;
     const float p = g.probs[d.off[3] + id];
     int fr[4];

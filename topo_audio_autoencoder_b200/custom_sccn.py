@@ -112,6 +112,11 @@ CONCURRENT_RANKS = os.environ.get("TOPO_CONCURRENT_RANKS", "1") not in ("0", "")
 # make the neighbourhood aggregation part of the same autograd node as the combine: its backward then works on the
 # node's own gradient buffers (no clones of the in-place updated ones, no zero fills, no autograd additions)
 FUSED_LAYER_NODE = True
+# Expected fraction of live rows per rank, for dividing the SMs between the four concurrent rank launches.  Buffers are
+# sized by the bound B * n_r and the live counts stay on the device (no host synchronisation), so the split needs an
+# estimate: 1.0 = every candidate simplex active (the shipped BinaryGumbel gate).  ComplexStage.calibrate() measures it
+# once on a representative batch (GraphedStep does so before capturing); a wrong estimate costs balance, never correctness.
+ROW_FRACTION_HINT = [1.0, 1.0, 1.0, 1.0]
 
 
 class _CombineFn(torch.autograd.Function):
@@ -309,7 +314,8 @@ class _LayerCombineFn(torch.autograd.Function):
         ch = per[0]["aggs"][0].shape[1]
         need_grad = SAVE_ACTIVATIONS and any(ctx.needs_input_grad)
         n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
-        tiles = [-(-pr["aggs"][0].shape[0] // 128) for pr in per]
+        tiles = [max(1, int(-(-pr["aggs"][0].shape[0] * ROW_FRACTION_HINT[r] // 128))) if pr["aggs"][0].shape[0] else 0
+                 for r, pr in enumerate(per)]
         costs = [t * (rc["n_msgs"] + 1.2) for t, rc in zip(tiles, ranks)]       # per tile: a fixed part + one part per message
         shares = _sm_shares(costs, n_sm, tiles)
         outs = []

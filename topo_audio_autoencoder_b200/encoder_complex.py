@@ -314,6 +314,17 @@ class ComplexStage(nn.Module):
         out.update(complex=cx, rectified=rect, vertex_penalty=vp, entropy_loss=ent)
         return out
 
+    @torch.no_grad()
+    def calibrate(self, logits: torch.Tensor, noise: Optional[torch.Tensor] = None) -> List[float]:
+        """Measure the live fraction of every rank on a representative batch (one host synchronisation) and store it as
+        the SM-split estimate of the concurrent rank launches (custom_sccn.ROW_FRACTION_HINT)."""
+        rect = self.head.rectified_batch(logits, noise)
+        cx = self.head.batched_complex(rect, sync=True)
+        totals = cx.host_counts.sum(dim=0).tolist()
+        bound = [logits.shape[0] * c for c in self.head._tables.counts]
+        _sccn.ROW_FRACTION_HINT[:] = [min(1.0, max(t / b, 1.0 / max(b, 1))) if b else 1.0 for t, b in zip(totals, bound)]
+        return list(_sccn.ROW_FRACTION_HINT)
+
     @staticmethod
     def split_per_sample(cx: BatchedComplex, x: torch.Tensor, rank: int) -> List[torch.Tensor]:
         if cx.host_counts is None:

@@ -49,6 +49,8 @@ class GraphedStep:
         self.graph = torch.cuda.CUDAGraph()
         self._baked = self._baked_state()
         self.captures += 1
+        if hasattr(self.stage, "calibrate"):        # live-row estimate for the SM split of the concurrent rank launches
+            self.stage.calibrate(self.logits.detach(), self.noise)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):          # warm-up off the capture: allocator, function attributes
