@@ -58,6 +58,18 @@ __device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity
     }
 }
 
+// ---- bulk asynchronous copies (the TMA engine's linear mode: cp.async.bulk, SASS UBLKCP) -------------------------
+// One thread arms the barrier with the byte count and issues the copies; the engine moves the data without occupying
+// a single LSU slot and completes the transaction count on the barrier.  dst / src / bytes: multiples of 16.
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
 // ---- named barriers: producers arrive without blocking, the consumer warp syncs ----------------
 __device__ __forceinline__ void named_bar_arrive(uint32_t id, uint32_t count) {
     asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
