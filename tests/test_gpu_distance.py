@@ -42,7 +42,10 @@ def test_full_length_clips_and_row_sharding():
     assert_close("distance/full-length-pairs", got, want, rtol=2e-5, atol=1e-6)
     shards = [prep.rows(*pd.shard_rows(70, r, 4)) for r in range(4)]
     assert torch.equal(torch.cat(shards), full)
-    assert torch.equal(full, full.t())
+    # both orientations of a pair are reduced; they agree to fp32 rounding and the dense product mirrors the upper one
+    assert_close("distance/orientation", full, full.t(), rtol=2e-6, atol=1e-6)
+    sym = pd.mirror_upper(full)
+    assert torch.equal(sym, sym.t()) and torch.equal(torch.triu(sym, 1), torch.triu(full, 1)) and (torch.diagonal(full) == 0).all()
 
 
 def test_streaming_topk_sweep_equals_the_dense_matrix():
@@ -103,3 +106,20 @@ def test_compute_distances_top_k_files(tmp_path):
         assert top[name]["sorted_distances"] == rec["sorted_distances"][:3]
         assert top[name]["index"] == rec["index"]
     assert torch.equal(torch.load(sdir / "distance_matrix.pt"), dense)
+
+
+def test_gram_term_keeps_fp32_accuracy_for_near_duplicates():
+    """The squared-difference term is mean x^2 + mean y^2 - 2 <x, y> / len with <x, y> on the tensor cores: duplicates and
+    near-duplicates (the pairs a nearest-neighbour search is about) are where that form cancels."""
+    from topo_audio_autoencoder_b200 import precompute_distances as pd
+    g = torch.Generator().manual_seed(21)
+    base = torch.randn(6, 1, 64000, generator=g) * 0.1
+    audio = torch.cat([base, base[:2].clone(), base[2:4] * 1.0005, base[4:6] + 1e-4 * torch.randn(2, 1, 64000, generator=g)])
+    got = pd.pairwise_spectral_distances(audio.cuda()).cpu()
+    pairs = [(0, 6), (1, 7), (2, 8), (3, 9), (4, 10), (5, 11), (0, 1), (6, 9)]
+    want = do.batch_audio_distance(audio[[a for a, _ in pairs]], audio[[b for _, b in pairs]])
+    mine = torch.stack([got[a, b] for a, b in pairs])
+    # exact duplicates: the true distance is 0; the two ways of summing x^2 (prepare kernel vs tensor cores) leave ~1e-6
+    assert mine[:2].abs().max().item() < 5e-6, mine[:2]
+    assert_close("distance/near-duplicates", mine[2:], want[2:], rtol=2e-5, atol=3e-6)
+    assert (got >= 0).all()

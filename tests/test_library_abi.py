@@ -65,7 +65,9 @@ def test_arguments_are_validated_before_cuda():
         check(lib.topo_tables_create_ex(0, 0, C.byref(C.c_void_p())))
     seg = (C.c_int64 * 5)(129150, 128763, 128757, 129129, 130065)
     dp = lib.topo_distance_padded_size(seg, 5)
-    assert dp % 16 == 0 and 645864 <= dp < 645864 + 5 * 16
+    assert dp % 64 == 0 and 645864 <= dp < 645864 + 5 * 64
+    assert lib.topo_distance_image_bytes(129, seg, 5) == 2 * (dp // 64) * 3 * 128 * 128
+    assert lib.topo_distance_workspace_floats(3, 7, 5) == 2 * 5 * 3 * 7
 
 
 def test_cpu_tensors_are_refused():

@@ -1,31 +1,42 @@
 // D1-D3: tiled pairwise multi-scale spectral distance.
-// Replaces the pair loop of compute_distances (precompute_distances.py:89-115), which recomputes
-// both multi-scale STFTs for every pair and scatters results in a Python loop.  Here the N
-// spectrograms are computed once (front half, host side), laid out as one padded row per clip, and a
-// 64 x 64 tile of pairs is reduced per CTA:
+// Replaces the pair loop of compute_distances (precompute_distances.py:89-115), which recomputes both multi-scale STFTs
+// for every pair and scatters results in a Python loop.  Here the N spectrograms are computed once (front half, host
+// side) and every pair is reduced from prepared operands:
 //     d(i,j) = sum_s [ mean_s((x-y)^2) / (mean_s(x^2) + 1e-7) + mean_s |log(x+eps) - log(y+eps)| ]
 // with x the LOWER-index clip (precompute_distances.py:89, 106-110), mirrored (:114-115).
-// FP32-ALU bound (4 instructions per pair-element; the L1-of-logs term is not a GEMM); operands are
-// staged through shared memory, k-major, so one LDS.128 feeds four pairs.  Two-level summation
-// (16-element stage sums folded into the per-scale accumulator) keeps fp32 error ~1e-6 relative.
+//
+// The two terms have different shapes and run on different pipes:
+//   * relative L2:  sum (x-y)^2 = sum x^2 + sum y^2 - 2 <x, y>.  The Gram term <x, y> is a GEMM with K = 645,864: it runs
+//     on the 5th-generation tensor cores as bf16x3 (tc16.cuh: three bf16 parts per fp32 value, six part products,
+//     fp32-accurate) -- `gram_kernel`: operand tiles are pre-swizzled images in global memory that the TMA engine streams
+//     into a two-stage shared-memory ring (cp.async.bulk + mbarrier transaction counts, one producer thread), one thread
+//     issues tcgen05.mma into a ping-pong pair of tensor-memory accumulators, eight warps drain them.  Accumulation is
+//     two-level so that a 130,000-term sum keeps fp32 accuracy: tensor memory holds 64 terms, registers 32 x 64,
+//     the output tile the rest.
+//   * L1 of logs:  sum |log x - log y| is not a GEMM -- `l1_kernel`: 2 FP32 instructions per pair-element on a 128 x 64
+//     pair tile, operands staged k-major through shared memory so one LDS.128 feeds four pairs, two-level sums.
+//   * `combine_kernel` folds both per scale with the lower-index clip's normaliser.
 #include <algorithm>
 
 #include "common.cuh"
+#include "tc16.cuh"
 
 namespace topo {
 namespace {
 
-constexpr int KC = 16;           // spectrogram bins per stage; every scale segment is padded to it
-constexpr int TI = 64;           // rows of the pair tile
-constexpr int TJ = 64;           // columns of the pair tile
-constexpr int LDI = TI + 4;      // padded strides of the k-major stages
-constexpr int LDJ = TJ + 4;
+using namespace tc16;
+
+constexpr int KC = 16;            // bins per stage of the L1 kernel
+constexpr int kChunk = 64;        // bins per k-chunk of the Gram kernel = one SWIZZLE_128B atom of bf16; segments are padded to it
+constexpr int kRowsPerBlock = 128;    // clips per image block = M and N of the Gram tile
 constexpr int kMaxScales = 8;
+constexpr uint32_t kPartBytes = kRowsPerBlock * 128;     // one bf16 part of a [128 x 64] chunk: 16 KB
+constexpr uint32_t kChunkBytes = 3 * kPartBytes;         // 48 KB per (clip block, k-chunk)
 
 struct Segments {
     long long len[kMaxScales];      // true length of each scale segment
     long long pad_off[kMaxScales];  // offset in the padded row
-    long long pad_len[kMaxScales];  // padded length (multiple of KC)
+    long long pad_len[kMaxScales];  // padded length (multiple of kChunk)
     long long src_off[kMaxScales];  // offset in the unpadded row
     int n;
     long long dp;                   // padded row length
@@ -37,7 +48,7 @@ Segments make_segments(const int64_t* seg_len, int n_scales) {
     long long po = 0, so = 0;
     for (int i = 0; i < n_scales; ++i) {
         s.len[i] = seg_len[i];
-        s.pad_len[i] = (seg_len[i] + KC - 1) / KC * KC;
+        s.pad_len[i] = (seg_len[i] + kChunk - 1) / kChunk * kChunk;
         s.pad_off[i] = po;
         s.src_off[i] = so;
         po += s.pad_len[i];
@@ -47,27 +58,35 @@ Segments make_segments(const int64_t* seg_len, int n_scales) {
     return s;
 }
 
-// one CTA per (clip, scale): padded copy, log(x + eps), mean of squares
-__global__ void __launch_bounds__(256) distance_prepare_kernel(const float* __restrict__ spec, long long d,
-                                                               Segments seg, float log_eps,
-                                                               float* __restrict__ spec_p,
-                                                               float* __restrict__ logspec_p,
-                                                               float* __restrict__ sq_mean) {
+// ------------------------------------------------------------------------------------------------------------------
+// prepare: one CTA per (clip, scale).  log(x + eps) padded row, mean of squares, and the bf16x3 image of the clip's row
+// inside its 128-clip block: image[block][k_chunk][part][row][64 bf16], rows swizzled exactly as tcgen05 wants them in
+// shared memory, so that a (block, k_chunk) operand tile is 48 contiguous kilobytes.
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) distance_prepare_kernel(const float* __restrict__ spec, long long d, Segments seg,
+                                                               float log_eps, float* __restrict__ logspec_p,
+                                                               uint8_t* __restrict__ image, float* __restrict__ sq_mean) {
     const long long clip = blockIdx.x;
     const int s = blockIdx.y;
     const float* src = spec + clip * d + seg.src_off[s];
-    float* dst = spec_p + clip * seg.dp + seg.pad_off[s];
     float* ldst = logspec_p + clip * seg.dp + seg.pad_off[s];
+    const long long n_chunks = seg.dp / kChunk;
+    const long long blk = clip / kRowsPerBlock;
+    const int row = static_cast<int>(clip % kRowsPerBlock);
+    uint8_t* img_block = image + blk * n_chunks * kChunkBytes;
     float acc = 0.f;
-    for (long long k = threadIdx.x; k < seg.pad_len[s]; k += blockDim.x) {
-        float v = 0.f, l = 0.f;
-        if (k < seg.len[s]) {
-            v = src[k];
-            l = logf(v + log_eps);
-            acc = fmaf(v, v, acc);
+    // one thread per group of eight consecutive bins = one 16-byte chunk of each bf16 part
+    for (long long k8 = threadIdx.x; k8 < seg.pad_len[s] / 8; k8 += blockDim.x) {
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const long long k = k8 * 8 + e;
+            v[e] = k < seg.len[s] ? src[k] : 0.f;
+            ldst[k] = k < seg.len[s] ? logf(v[e] + log_eps) : 0.f;   // padding: 0 in both arrays, contributes to neither sum
+            acc = fmaf(v[e], v[e], acc);
         }
-        dst[k] = v;     // padding: both arrays 0, so padded bins contribute nothing to either sum
-        ldst[k] = l;
+        const long long kk = seg.pad_off[s] + k8 * 8;                 // position in the padded row
+        store_split8(img_block + (kk / kChunk) * kChunkBytes, kPartBytes, row, static_cast<int>((kk % kChunk) / 8), v);
     }
     __shared__ float red[8];
     acc = warp_sum(acc);
@@ -80,69 +99,198 @@ __global__ void __launch_bounds__(256) distance_prepare_kernel(const float* __re
     }
 }
 
-struct Stage {
-    float x[KC * LDI];
-    float lx[KC * LDI];
-    float y[KC * LDJ];
-    float ly[KC * LDJ];
-};
-
-// 256 threads: ty = tid / 16 owns rows ty*4..+3, tx = tid % 16 owns columns tx*4..+3
 // Rows and columns may come from DIFFERENT prepared blocks (streaming sweep: a resident row block against column blocks
-// prepared on the fly): `rows` holds clips [row_g0, row_g0 + n_rows) of the collection, `cols` clips [col_g0, col_g0 +
-// n_cols); the kernel reduces rows [row_begin, row_end) x columns [col_begin, col_end) given as LOCAL indices.
+// prepared on the fly): an operand holds clips [g0, g0 + count) of the collection.
 struct DistOperand {
-    const float* spec;      // [count, dp] padded spectrogram rows
-    const float* logspec;   // [count, dp] log(x + eps)
+    const float* logspec;   // [count, dp]
+    const uint8_t* image;   // [ceil(count / 128)][dp / 64] chunks of 48 KB
     const float* sq_mean;   // [count, n_scales]
     long long count;        // clips in this block
     long long g0;           // index of its first clip in the whole collection
 };
 
-__global__ void __launch_bounds__(256) distance_rows_kernel(DistOperand rows, DistOperand cols, Segments seg,
-                                                               long long row_begin, long long row_end,
-                                                               long long col_begin, long long col_end,
-                                                               float* __restrict__ out, long long ld_out) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    Stage* st = reinterpret_cast<Stage*>(smem_raw);   // [2]
+// ------------------------------------------------------------------------------------------------------------------
+// Gram term on the tensor cores.  grid = (column tiles, row tiles, scales); a CTA owns the 128 x 128 tile of <x, y> of one
+// scale.  Warp 8 lane 0: producer (cp.async.bulk of the two 48 KB operand chunks of a stage).  Warp 9 lane 0: issues the
+// 24 MMAs of a chunk (4 k-steps x 6 part products) into accumulator (chunk & 1).  Warps 0..7: drain that accumulator into
+// registers (warp w: TMEM lane quarter w % 4, columns 64 (w / 4) ..), fold the registers into the output tile every 32
+// chunks.  Nothing waits for anything but its own mbarrier.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kGramStages = 2;
+constexpr int kGramThreads = 320;
+constexpr int kFold = 32;          // chunks accumulated in registers between two folds into the output tile
+
+struct GramSmem {
+    static constexpr uint32_t kStage = 2 * kChunkBytes;                  // A then B
+    static constexpr uint32_t kBar = kGramStages * kStage;               // full[2], empty[2], acc_full[2], acc_empty[2], tmem base
+    static constexpr uint32_t kTotal = kBar + 128;
+};
+
+__global__ void __launch_bounds__(kGramThreads, 1) gram_kernel(DistOperand rows, DistOperand cols, Segments seg,
+                                                               long long row_tile0, long long col_tile0, long long n_rows_out,
+                                                               long long n_cols_out, long long row_begin, long long col_begin,
+                                                               float* __restrict__ gram /* [scales][n_rows_out][n_cols_out] */) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* base = smem_raw;
+    uint64_t* full = reinterpret_cast<uint64_t*>(base + GramSmem::kBar);
+    uint64_t* empty = full + 2;
+    uint64_t* acc_full = full + 4;
+    uint64_t* acc_empty = full + 6;
+    uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(full + 8);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int s = blockIdx.z;
+    const long long rt = row_tile0 + blockIdx.y, ct = col_tile0 + blockIdx.x;       // 128-clip blocks of the two operands
+    const long long n_chunks_total = seg.dp / kChunk;
+    const long long c0 = seg.pad_off[s] / kChunk, n_chunks = seg.pad_len[s] / kChunk;
+    const uint8_t* a_src = rows.image + (rt * n_chunks_total + c0) * kChunkBytes;
+    const uint8_t* b_src = cols.image + (ct * n_chunks_total + c0) * kChunkBytes;
+
+    if (tid == 0) {
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], 1);
+            mbar_init(&acc_full[i], 1);
+            mbar_init(&acc_empty[i], 8);          // one arrival per draining warp
+        }
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc(tmem_base_smem, 256);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_base_smem;
+
+    if (warp == 8) {
+        if (lane == 0) {
+            for (long long c = 0; c < n_chunks; ++c) {
+                const int st = static_cast<int>(c & 1);
+                if (c >= kGramStages) mbar_wait_backoff(&empty[st], static_cast<uint32_t>(((c >> 1) - 1) & 1));
+                uint8_t* dst = base + st * GramSmem::kStage;
+                mbar_arrive_expect_tx(&full[st], 2 * kChunkBytes);
+#pragma unroll
+                for (int p = 0; p < 3; ++p) {
+                    bulk_copy_g2s(dst + p * kPartBytes, a_src + c * kChunkBytes + p * kPartBytes, kPartBytes, &full[st]);
+                    bulk_copy_g2s(dst + kChunkBytes + p * kPartBytes, b_src + c * kChunkBytes + p * kPartBytes, kPartBytes, &full[st]);
+                }
+            }
+        }
+    } else if (warp == 9) {
+        if (lane == 0) {
+            for (long long c = 0; c < n_chunks; ++c) {
+                const int st = static_cast<int>(c & 1);
+                mbar_wait_backoff(&full[st], static_cast<uint32_t>((c >> 1) & 1));
+                if (c >= 2) mbar_wait_backoff(&acc_empty[st], static_cast<uint32_t>(((c >> 1) - 1) & 1));
+                tc_fence_after_sync();
+                const uint32_t a_s = smem_u32(base + st * GramSmem::kStage);
+                gemm_bf16x3_unrolled<kChunk / 16>(tmem_base + st * 128, k_major(a_s, kRowsPerBlock), k_major(a_s + kChunkBytes, kRowsPerBlock),
+                                                  idesc_bf16(128, 128, 0, 0), 0);
+                mma_commit(&empty[st]);           // the stage's operand tiles may be overwritten
+                mma_commit(&acc_full[st]);        // the accumulator holds this chunk's 64-term partial products
+            }
+        }
+    } else {
+        // ---- drain: thread (lane quarter w % 4, lane) = tile row, columns [64 (w / 4), +64) ----
+        const int half = warp >> 2;
+        const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
+        const long long row = rt * kRowsPerBlock + (warp & 3) * 32 + lane - row_begin;         // row of the output tile
+        const long long col0 = ct * kRowsPerBlock + half * 64 - col_begin;
+        const bool row_ok = row >= 0 && row < n_rows_out;
+        float* out_row = gram + (static_cast<long long>(s) * n_rows_out + (row_ok ? row : 0)) * n_cols_out;
+        float lo[64];
+#pragma unroll
+        for (int i = 0; i < 64; ++i) lo[i] = 0.f;
+        bool first_fold = true;
+        auto fold = [&]() {
+            if (row_ok) {
+#pragma unroll
+                for (int i = 0; i < 64; ++i) {
+                    const long long col = col0 + i;
+                    if (col >= 0 && col < n_cols_out) out_row[col] = first_fold ? lo[i] : out_row[col] + lo[i];
+                }
+            }
+            first_fold = false;
+#pragma unroll
+            for (int i = 0; i < 64; ++i) lo[i] = 0.f;
+        };
+        for (long long c = 0; c < n_chunks; ++c) {
+            const int st = static_cast<int>(c & 1);
+            mbar_wait_backoff(&acc_full[st], static_cast<uint32_t>((c >> 1) & 1));
+            tc_fence_after_sync();
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float v[16];
+                uint32_t r[16];
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                      "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                    : "r"(tmem_base + st * 128 + lane_addr + half * 64 + q * 16)
+                    : "memory");
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    v[i] = __uint_as_float(r[i]);
+                    lo[q * 16 + i] += v[i];
+                }
+            }
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) {
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[st])) : "memory");
+            }
+            if (((c + 1) % kFold) == 0) fold();
+        }
+        fold();
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, 256);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// L1 of logs on the FP32 pipe: 128 x 64 pair tile, 256 threads, thread (ty, tx) = (tid / 16, tid % 16) owns rows
+// 8 ty .. +7 and columns 4 tx .. +3.  l1[scale][i][j] = sum_k |lx_ik - ly_jk| (not yet divided by the segment length).
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int TI = 128, TJ = 64;
+constexpr int LDI = TI + 4, LDJ = TJ + 4;
+
+struct L1Stage {
+    float lx[KC * LDI];
+    float ly[KC * LDJ];
+};
+
+__global__ void __launch_bounds__(256) l1_kernel(DistOperand rows, DistOperand cols, Segments seg, long long row_begin,
+                                                 long long row_end, long long col_begin, long long col_end,
+                                                 float* __restrict__ l1_out /* [scales][rows][cols] */) {
+    __shared__ __align__(16) L1Stage st[2];
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const long long i0 = row_begin + static_cast<long long>(blockIdx.y) * TI;
     const long long j0 = col_begin + static_cast<long long>(blockIdx.x) * TJ;
+    const long long n_rows_out = row_end - row_begin, n_cols_out = col_end - col_begin;
 
-    // loader role: 4 threads per row fetch 16 consecutive bins (one float4 each) of that row
+    // loader role: 4 threads per row fetch 16 consecutive bins (one float4 each); rows tid / 4 and tid / 4 + 64 of the
+    // row tile, row tid / 4 of the column tile
     const int l_row = tid >> 2, l_k = (tid & 3) * 4;
-    const long long gi = min(i0 + l_row, rows.count - 1);
-    const long long gj = min(j0 + l_row, cols.count - 1);
-    const float* px = rows.spec + gi * seg.dp + l_k;
-    const float* plx = rows.logspec + gi * seg.dp + l_k;
-    const float* py = cols.spec + gj * seg.dp + l_k;
-    const float* ply = cols.logspec + gj * seg.dp + l_k;
-
-    float4 r[4];
+    const float* px0 = rows.logspec + min(i0 + l_row, rows.count - 1) * seg.dp + l_k;
+    const float* px1 = rows.logspec + min(i0 + l_row + 64, rows.count - 1) * seg.dp + l_k;
+    const float* py = cols.logspec + min(j0 + l_row, cols.count - 1) * seg.dp + l_k;
+    float4 r[3];
     auto fetch = [&](long long k0) {
-        r[0] = __ldg(reinterpret_cast<const float4*>(px + k0));
-        r[1] = __ldg(reinterpret_cast<const float4*>(plx + k0));
+        r[0] = __ldg(reinterpret_cast<const float4*>(px0 + k0));
+        r[1] = __ldg(reinterpret_cast<const float4*>(px1 + k0));
         r[2] = __ldg(reinterpret_cast<const float4*>(py + k0));
-        r[3] = __ldg(reinterpret_cast<const float4*>(ply + k0));
     };
-    auto scatter = [&](float* base, int ld, int row, const float4& v) {
-        base[(l_k + 0) * ld + row] = v.x;
-        base[(l_k + 1) * ld + row] = v.y;
-        base[(l_k + 2) * ld + row] = v.z;
-        base[(l_k + 3) * ld + row] = v.w;
+    auto scatter = [&](float* b, int ld, int row, const float4& v) {
+        b[(l_k + 0) * ld + row] = v.x;
+        b[(l_k + 1) * ld + row] = v.y;
+        b[(l_k + 2) * ld + row] = v.z;
+        b[(l_k + 3) * ld + row] = v.w;
     };
-    auto deposit = [&](Stage& s) {
-        scatter(s.x, LDI, l_row, r[0]);
-        scatter(s.lx, LDI, l_row, r[1]);
-        scatter(s.y, LDJ, l_row, r[2]);
-        scatter(s.ly, LDJ, l_row, r[3]);
+    auto deposit = [&](L1Stage& s) {
+        scatter(s.lx, LDI, l_row, r[0]);
+        scatter(s.lx, LDI, l_row + 64, r[1]);
+        scatter(s.ly, LDJ, l_row, r[2]);
     };
-
-    float dist[4][4];
-#pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) dist[a][c] = 0.f;
 
     const long long stages_total = seg.dp / KC;
     fetch(0);
@@ -150,73 +298,100 @@ __global__ void __launch_bounds__(256) distance_rows_kernel(DistOperand rows, Di
     __syncthreads();
     long long g = 0;
     for (int s = 0; s < seg.n; ++s) {
-        float sq[4][4], l1[4][4];
+        float l1[8][4];
 #pragma unroll
-        for (int a = 0; a < 4; ++a)
+        for (int a = 0; a < 8; ++a)
 #pragma unroll
-            for (int c = 0; c < 4; ++c) sq[a][c] = l1[a][c] = 0.f;
+            for (int c = 0; c < 4; ++c) l1[a][c] = 0.f;
         const long long stages = seg.pad_len[s] / KC;
         for (long long q = 0; q < stages; ++q, ++g) {
-            const Stage& cur = st[g & 1];
+            const L1Stage& cur = st[g & 1];
             const bool more = (g + 1) < stages_total;
             if (more) fetch((g + 1) * KC);
-            float sq_i[4][4], l1_i[4][4];
+            float l1_i[8][4];
 #pragma unroll
-            for (int a = 0; a < 4; ++a)
+            for (int a = 0; a < 8; ++a)
 #pragma unroll
-                for (int c = 0; c < 4; ++c) sq_i[a][c] = l1_i[a][c] = 0.f;
+                for (int c = 0; c < 4; ++c) l1_i[a][c] = 0.f;
 #pragma unroll 4
             for (int k = 0; k < KC; ++k) {
-                const float4 xv = *reinterpret_cast<const float4*>(cur.x + k * LDI + ty * 4);
-                const float4 lxv = *reinterpret_cast<const float4*>(cur.lx + k * LDI + ty * 4);
-                const float4 y0 = *reinterpret_cast<const float4*>(cur.y + k * LDJ + tx * 4);
-                const float4 ly0 = *reinterpret_cast<const float4*>(cur.ly + k * LDJ + tx * 4);
-                const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, lxs[4] = {lxv.x, lxv.y, lxv.z, lxv.w};
-                const float ys[4] = {y0.x, y0.y, y0.z, y0.w};
-                const float lys[4] = {ly0.x, ly0.y, ly0.z, ly0.w};
+                const float4 xa = *reinterpret_cast<const float4*>(cur.lx + k * LDI + ty * 8);
+                const float4 xb = *reinterpret_cast<const float4*>(cur.lx + k * LDI + ty * 8 + 4);
+                const float4 yv = *reinterpret_cast<const float4*>(cur.ly + k * LDJ + tx * 4);
+                const float xs[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+                const float ys[4] = {yv.x, yv.y, yv.z, yv.w};
 #pragma unroll
-                for (int a = 0; a < 4; ++a)
+                for (int a = 0; a < 8; ++a)
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        const float dd = xs[a] - ys[c];
-                        sq_i[a][c] = fmaf(dd, dd, sq_i[a][c]);
-                        l1_i[a][c] += fabsf(lxs[a] - lys[c]);
-                    }
+                    for (int c = 0; c < 4; ++c) l1_i[a][c] += fabsf(xs[a] - ys[c]);
             }
 #pragma unroll
-            for (int a = 0; a < 4; ++a)
+            for (int a = 0; a < 8; ++a)
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    sq[a][c] += sq_i[a][c];
-                    l1[a][c] += l1_i[a][c];
-                }
+                for (int c = 0; c < 4; ++c) l1[a][c] += l1_i[a][c];
             if (more) deposit(st[(g + 1) & 1]);
             __syncthreads();
         }
-        // fold this scale: the normaliser belongs to the lower-index clip of the pair (collection-wide indices)
-        const float inv_len = 1.0f / static_cast<float>(seg.len[s]);
 #pragma unroll
-        for (int a = 0; a < 4; ++a) {
-            const long long i = min(i0 + ty * 4 + a, rows.count - 1);
+        for (int a = 0; a < 8; ++a) {
+            const long long i = i0 + ty * 8 + a;
+            if (i >= row_end) continue;
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-                const long long j = min(j0 + tx * 4 + c, cols.count - 1);
-                const bool row_is_lower = rows.g0 + i <= cols.g0 + j;
-                const float norm = (row_is_lower ? __ldg(rows.sq_mean + i * seg.n + s) : __ldg(cols.sq_mean + j * seg.n + s)) + 1e-7f;
-                dist[a][c] += (sq[a][c] * inv_len) / norm + l1[a][c] * inv_len;
+                const long long j = j0 + tx * 4 + c;
+                if (j < col_end) l1_out[(static_cast<long long>(s) * n_rows_out + (i - row_begin)) * n_cols_out + (j - col_begin)] = l1[a][c];
             }
         }
     }
-#pragma unroll
-    for (int a = 0; a < 4; ++a) {
-        const long long i = i0 + ty * 4 + a;
-        if (i >= row_end) continue;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            const long long j = j0 + tx * 4 + c;
-            if (j < col_end) out[(i - row_begin) * ld_out + (j - col_begin)] = (rows.g0 + i == cols.g0 + j) ? 0.f : dist[a][c];
-        }
+}
+
+// d(i,j) = sum_s [ (Sx_i + Sy_j - 2 G_ij) / len_s / (norm_lower + 1e-7) + L1_ij / len_s ],  S = len_s * mean square
+__global__ void __launch_bounds__(256) combine_kernel(DistOperand rows, DistOperand cols, Segments seg, long long row_begin,
+                                                      long long n_rows_out, long long col_begin, long long n_cols_out,
+                                                      const float* __restrict__ gram, const float* __restrict__ l1,
+                                                      float* __restrict__ out, long long ld_out) {
+    const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    if (idx >= n_rows_out * n_cols_out) return;
+    const long long i = idx / n_cols_out, j = idx % n_cols_out;
+    const long long li = row_begin + i, lj = col_begin + j;
+    const bool row_is_lower = rows.g0 + li <= cols.g0 + lj;
+    float dist = 0.f;
+    for (int s = 0; s < seg.n; ++s) {
+        const float mx = __ldg(rows.sq_mean + li * seg.n + s), my = __ldg(cols.sq_mean + lj * seg.n + s);
+        const float len = static_cast<float>(seg.len[s]);
+        const float g = gram[(static_cast<long long>(s) * n_rows_out + i) * n_cols_out + j];
+        // mean((x - y)^2) = mean x^2 + mean y^2 - 2 <x, y> / len, never negative
+        const float msq = fmaxf((mx + my) - 2.0f * (g / len), 0.f);
+        const float norm = (row_is_lower ? mx : my) + 1e-7f;
+        dist += msq / norm + l1[(static_cast<long long>(s) * n_rows_out + i) * n_cols_out + j] / len;
     }
+    out[i * ld_out + j] = (rows.g0 + li == cols.g0 + lj) ? 0.f : dist;
+}
+
+int launch_distance(const DistOperand& rows, const DistOperand& cols, const Segments& seg, int64_t row_begin, int64_t row_end,
+                    int64_t col_begin, int64_t col_end, float* workspace, float* out, int64_t ld_out, topo_stream_t stream) {
+    const int64_t nr = row_end - row_begin, nc = col_end - col_begin;
+    float* gram = workspace;
+    float* l1 = workspace + static_cast<int64_t>(seg.n) * nr * nc;
+    cudaStream_t s = as_stream(stream);
+    {
+        const int64_t rt0 = row_begin / kRowsPerBlock, rt1 = (row_end + kRowsPerBlock - 1) / kRowsPerBlock;
+        const int64_t ct0 = col_begin / kRowsPerBlock, ct1 = (col_end + kRowsPerBlock - 1) / kRowsPerBlock;
+        if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(gram_kernel), GramSmem::kTotal)) return rc;
+        const dim3 grid(static_cast<unsigned>(ct1 - ct0), static_cast<unsigned>(rt1 - rt0), static_cast<unsigned>(seg.n));
+        gram_kernel<<<grid, kGramThreads, GramSmem::kTotal, s>>>(rows, cols, seg, rt0, ct0, nr, nc, row_begin, col_begin, gram);
+    }
+    {
+        const dim3 grid(static_cast<unsigned>((nc + TJ - 1) / TJ), static_cast<unsigned>((nr + TI - 1) / TI));
+        l1_kernel<<<grid, 256, 0, s>>>(rows, cols, seg, row_begin, row_end, col_begin, col_end, l1);
+    }
+    {
+        const int64_t total = nr * nc;
+        combine_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(rows, cols, seg, row_begin, nr, col_begin, nc, gram, l1,
+                                                                                   out, ld_out);
+    }
+    TOPO_LAUNCH_CHECK();
+    return TOPO_OK;
 }
 
 }  // namespace
@@ -229,12 +404,23 @@ extern "C" int64_t topo_distance_padded_size(const int64_t* seg_len, int n_scale
     return make_segments(seg_len, n_scales).dp;
 }
 
+extern "C" int64_t topo_distance_image_bytes(int64_t n, const int64_t* seg_len, int n_scales) {
+    if (!seg_len || n_scales < 1 || n_scales > kMaxScales || n < 0) return -1;
+    const Segments seg = make_segments(seg_len, n_scales);
+    return (n + kRowsPerBlock - 1) / kRowsPerBlock * (seg.dp / kChunk) * static_cast<int64_t>(kChunkBytes);
+}
+
+extern "C" int64_t topo_distance_workspace_floats(int64_t n_rows, int64_t n_cols, int n_scales) {
+    if (n_rows < 0 || n_cols < 0 || n_scales < 1 || n_scales > kMaxScales) return -1;
+    return 2 * static_cast<int64_t>(n_scales) * n_rows * n_cols;
+}
+
 extern "C" int topo_distance_prepare(const float* spec, int64_t n, int64_t d, const int64_t* seg_len, int n_scales,
-                                     float log_eps, float* spec_p, float* logspec_p, float* sq_mean,
-                                     topo_stream_t stream) {
-    TOPO_REQUIRE(spec && seg_len && spec_p && logspec_p && sq_mean, "null argument");
+                                     float log_eps, float* logspec_p, void* image, float* sq_mean, topo_stream_t stream) {
+    TOPO_REQUIRE(spec && seg_len && logspec_p && image && sq_mean, "null argument");
     TOPO_REQUIRE(n_scales >= 1 && n_scales <= kMaxScales, "n_scales must be in [1, 8]");
     TOPO_REQUIRE(n >= 0 && n < (int64_t(1) << 31), "bad n");
+    TOPO_REQUIRE((reinterpret_cast<uintptr_t>(image) & 1023) == 0, "the operand image must be 1024-byte aligned");
     const Segments seg = make_segments(seg_len, n_scales);
     int64_t total = 0;
     for (int i = 0; i < n_scales; ++i) {
@@ -244,45 +430,35 @@ extern "C" int topo_distance_prepare(const float* spec, int64_t n, int64_t d, co
     TOPO_REQUIRE(total == d, "segment lengths do not add up to d");
     if (n == 0) return TOPO_OK;
     distance_prepare_kernel<<<dim3(static_cast<unsigned>(n), n_scales), 256, 0, as_stream(stream)>>>(
-        spec, d, seg, log_eps, spec_p, logspec_p, sq_mean);
+        spec, d, seg, log_eps, logspec_p, static_cast<uint8_t*>(image), sq_mean);
     TOPO_LAUNCH_CHECK();
     return TOPO_OK;
 }
 
-static int launch_distance(const DistOperand& rows, const DistOperand& cols, const Segments& seg, int64_t row_begin,
-                           int64_t row_end, int64_t col_begin, int64_t col_end, float* out, int64_t ld_out, topo_stream_t stream) {
-    const dim3 grid(static_cast<unsigned>((col_end - col_begin + TJ - 1) / TJ),
-                    static_cast<unsigned>((row_end - row_begin + TI - 1) / TI));
-    if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(distance_rows_kernel), 2 * sizeof(Stage))) return rc;
-    distance_rows_kernel<<<grid, 256, 2 * sizeof(Stage), as_stream(stream)>>>(rows, cols, seg, row_begin, row_end, col_begin,
-                                                                               col_end, out, ld_out);
-    TOPO_LAUNCH_CHECK();
-    return TOPO_OK;
-}
-
-extern "C" int topo_distance_rows(const float* spec_p, const float* logspec_p, const float* sq_mean, int64_t n,
+extern "C" int topo_distance_rows(const float* logspec_p, const void* image, const float* sq_mean, int64_t n,
                                   const int64_t* seg_len, int n_scales, int64_t row_begin, int64_t row_end,
-                                  int64_t col_begin, int64_t col_end, float* out, topo_stream_t stream) {
-    TOPO_REQUIRE(spec_p && logspec_p && sq_mean && seg_len && out, "null argument");
+                                  int64_t col_begin, int64_t col_end, float* workspace, float* out, topo_stream_t stream) {
+    TOPO_REQUIRE(logspec_p && image && sq_mean && seg_len && workspace && out, "null argument");
     TOPO_REQUIRE(n_scales >= 1 && n_scales <= kMaxScales, "n_scales must be in [1, 8]");
     TOPO_REQUIRE(0 <= row_begin && row_begin <= row_end && row_end <= n, "bad row range");
     TOPO_REQUIRE(0 <= col_begin && col_begin <= col_end && col_end <= n, "bad column range");
     if (row_begin == row_end || col_begin == col_end) return TOPO_OK;
     const Segments seg = make_segments(seg_len, n_scales);
-    const DistOperand all{spec_p, logspec_p, sq_mean, n, 0};
-    return launch_distance(all, all, seg, row_begin, row_end, col_begin, col_end, out, col_end - col_begin, stream);
+    const DistOperand all{logspec_p, static_cast<const uint8_t*>(image), sq_mean, n, 0};
+    return launch_distance(all, all, seg, row_begin, row_end, col_begin, col_end, workspace, out, col_end - col_begin, stream);
 }
 
-extern "C" int topo_distance_block(const float* row_spec, const float* row_logspec, const float* row_sq_mean, int64_t n_rows,
-                                   int64_t row_global0, const float* col_spec, const float* col_logspec,
+extern "C" int topo_distance_block(const float* row_logspec, const void* row_image, const float* row_sq_mean, int64_t n_rows,
+                                   int64_t row_global0, const float* col_logspec, const void* col_image,
                                    const float* col_sq_mean, int64_t n_cols, int64_t col_global0, const int64_t* seg_len,
-                                   int n_scales, float* out, int64_t ld_out, topo_stream_t stream) {
-    TOPO_REQUIRE(row_spec && row_logspec && row_sq_mean && col_spec && col_logspec && col_sq_mean && seg_len && out, "null argument");
+                                   int n_scales, float* workspace, float* out, int64_t ld_out, topo_stream_t stream) {
+    TOPO_REQUIRE(row_logspec && row_image && row_sq_mean && col_logspec && col_image && col_sq_mean && seg_len && workspace && out,
+                 "null argument");
     TOPO_REQUIRE(n_scales >= 1 && n_scales <= kMaxScales, "n_scales must be in [1, 8]");
     TOPO_REQUIRE(n_rows >= 0 && n_cols >= 0 && row_global0 >= 0 && col_global0 >= 0 && ld_out >= n_cols, "bad block geometry");
     if (n_rows == 0 || n_cols == 0) return TOPO_OK;
     const Segments seg = make_segments(seg_len, n_scales);
-    const DistOperand rows{row_spec, row_logspec, row_sq_mean, n_rows, row_global0};
-    const DistOperand cols{col_spec, col_logspec, col_sq_mean, n_cols, col_global0};
-    return launch_distance(rows, cols, seg, 0, n_rows, 0, n_cols, out, ld_out, stream);
+    const DistOperand rows{row_logspec, static_cast<const uint8_t*>(row_image), row_sq_mean, n_rows, row_global0};
+    const DistOperand cols{col_logspec, static_cast<const uint8_t*>(col_image), col_sq_mean, n_cols, col_global0};
+    return launch_distance(rows, cols, seg, 0, n_rows, 0, n_cols, workspace, out, ld_out, stream);
 }

@@ -55,46 +55,61 @@ def multiscale_spectrograms(audio: torch.Tensor, scales: Sequence[int] = SCALES)
 
 
 class PreparedSpectra:
-    """Padded spectrogram rows, their logs and per-scale mean squares, resident on the device."""
+    """Operands of the pair reduction for one block of clips, resident on the device: the padded logs (FP32 pipe, L1 term),
+    the bf16x3 operand image of the spectra (tensor cores, Gram term; csrc/distance.cu) and per-scale mean squares."""
 
     def __init__(self, spec: torch.Tensor, seg_len: Sequence[int], log_eps: float = LOG_EPSILON):
         spec = spec.contiguous()
         self.n, self.d = spec.shape
         self.seg_len = [int(s) for s in seg_len]
         self.seg_c = i64_array(self.seg_len)
-        self.dp = int(lib.topo_distance_padded_size(self.seg_c, len(self.seg_len)))
+        n_scales = len(self.seg_len)
+        self.dp = int(lib.topo_distance_padded_size(self.seg_c, n_scales))
         if self.dp < 0:
             raise ValueError("between 1 and 8 scales are supported")
         dev = spec.device
-        self.spec_p = torch.empty(self.n, self.dp, dtype=torch.float32, device=dev)
         self.logspec_p = torch.empty(self.n, self.dp, dtype=torch.float32, device=dev)
-        self.sq_mean = torch.empty(self.n, len(self.seg_len), dtype=torch.float32, device=dev)
-        check(lib.topo_distance_prepare(ptr(spec), self.n, self.d, self.seg_c, len(self.seg_len), float(log_eps),
-                                        ptr(self.spec_p), ptr(self.logspec_p), ptr(self.sq_mean), stream()))
+        image_bytes = int(lib.topo_distance_image_bytes(self.n, self.seg_c, n_scales))
+        # rows past n in the last 128-clip block must read as zero; cudaMalloc'ed tensors are at least 512-byte aligned and
+        # the caching allocator hands out 512-byte multiples: over-allocate to reach the 1024-byte alignment of the image
+        raw = (torch.zeros if self.n % 128 else torch.empty)(image_bytes + 1024, dtype=torch.uint8, device=dev)
+        shift = (-raw.data_ptr()) % 1024
+        self._image_raw = raw
+        self.image = raw[shift:shift + image_bytes]
+        self.sq_mean = torch.empty(self.n, n_scales, dtype=torch.float32, device=dev)
+        check(lib.topo_distance_prepare(ptr(spec), self.n, self.d, self.seg_c, n_scales, float(log_eps),
+                                        ptr(self.logspec_p), self.image.data_ptr(), ptr(self.sq_mean), stream()))
+
+    def _workspace(self, n_rows: int, n_cols: int) -> torch.Tensor:
+        words = int(lib.topo_distance_workspace_floats(n_rows, n_cols, len(self.seg_len)))
+        return torch.empty(max(words, 1), dtype=torch.float32, device=self.logspec_p.device)
 
     def block(self, cols: "PreparedSpectra", row_global0: int = 0, col_global0: int = 0,
-              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+              out: Optional[torch.Tensor] = None, workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
         """All pairs (row clip of self, column clip of `cols`) -> [self.n, cols.n].  The two blocks are slices
         [row_global0, ...) and [col_global0, ...) of one collection: the collection-wide indices decide which clip of a
         pair supplies the normaliser (the lower one, reference :89, :106-110) and where the zero diagonal is."""
         if cols.seg_len != self.seg_len:
             raise ValueError("row and column blocks were prepared with different scale segments")
         if out is None:
-            out = torch.empty(self.n, cols.n, dtype=torch.float32, device=self.spec_p.device)
+            out = torch.empty(self.n, cols.n, dtype=torch.float32, device=self.logspec_p.device)
         # `out` may be a column window of a wider buffer (the running top-k merge): unit column stride, any row stride
         if not (out.is_cuda and out.dtype == torch.float32 and out.dim() == 2 and out.stride(1) == 1
                 and out.shape[0] >= self.n and out.shape[1] >= cols.n):
             raise ValueError("out must be a CUDA float32 [rows, >= columns] view with unit column stride")
-        check(lib.topo_distance_block(ptr(self.spec_p), ptr(self.logspec_p), ptr(self.sq_mean), self.n, int(row_global0),
-                                      ptr(cols.spec_p), ptr(cols.logspec_p), ptr(cols.sq_mean), cols.n, int(col_global0),
-                                      self.seg_c, len(self.seg_len), out.data_ptr(), out.stride(0), stream()))
+        if workspace is None:
+            workspace = self._workspace(self.n, cols.n)
+        check(lib.topo_distance_block(ptr(self.logspec_p), self.image.data_ptr(), ptr(self.sq_mean), self.n, int(row_global0),
+                                      ptr(cols.logspec_p), cols.image.data_ptr(), ptr(cols.sq_mean), cols.n, int(col_global0),
+                                      self.seg_c, len(self.seg_len), ptr(workspace), out.data_ptr(), out.stride(0), stream()))
         return out
 
     def rows(self, row_begin: int, row_end: int, col_begin: int = 0, col_end: Optional[int] = None) -> torch.Tensor:
         col_end = self.n if col_end is None else col_end
-        out = torch.empty(row_end - row_begin, col_end - col_begin, dtype=torch.float32, device=self.spec_p.device)
-        check(lib.topo_distance_rows(ptr(self.spec_p), ptr(self.logspec_p), ptr(self.sq_mean), self.n, self.seg_c,
-                                     len(self.seg_len), row_begin, row_end, col_begin, col_end, ptr(out), stream()))
+        out = torch.empty(row_end - row_begin, col_end - col_begin, dtype=torch.float32, device=self.logspec_p.device)
+        workspace = self._workspace(row_end - row_begin, col_end - col_begin)
+        check(lib.topo_distance_rows(ptr(self.logspec_p), self.image.data_ptr(), ptr(self.sq_mean), self.n, self.seg_c,
+                                     len(self.seg_len), row_begin, row_end, col_begin, col_end, ptr(workspace), ptr(out), stream()))
         return out
 
 
@@ -104,7 +119,19 @@ def pairwise_spectral_distances(audio: torch.Tensor, scales: Sequence[int] = SCA
     spec, seg = multiscale_spectrograms(audio, scales)
     prep = PreparedSpectra(spec, seg)
     lo, hi = shard_rows(prep.n, rank, world_size)
-    return prep.rows(lo, hi)
+    out = prep.rows(lo, hi)
+    if world_size == 1:
+        out = mirror_upper(out)
+    return out
+
+
+def mirror_upper(distances: torch.Tensor) -> torch.Tensor:
+    """reference :113-115: only the pairs i < j are computed (x = the lower-index clip) and mirrored.  The kernels reduce
+    both orientations of a pair; they agree to fp32 rounding (the six bf16 part products of the Gram term are accumulated
+    in an order that depends on which clip is the row), so the exact mirror of the upper triangle is taken here.  A
+    row-sharded rank holds only its own rows and keeps both orientations as computed."""
+    upper = torch.triu(distances, diagonal=1)
+    return upper + upper.t()
 
 
 def shard_rows(n: int, rank: int, world_size: int):
@@ -146,7 +173,7 @@ def spectral_topk(audio: torch.Tensor, k: int, row_block: int = 1024, col_block:
         return vals, idx
     col_starts = list(range(0, n, col_block))
     probe = prepare_block(audio[:1], device, scales)
-    per_clip = 2 * probe.dp * 4
+    per_clip = probe.dp * 10                          # fp32 logs + three bf16 parts
     cached = None
     if n * per_clip <= cache_bytes:
         cached = [prepare_block(audio[c0:c0 + col_block], device, scales) for c0 in col_starts]
