@@ -129,25 +129,41 @@ def run_distance(args):
     value = pairs_per_step * args.steps / (ms * 1e-3)
     e2e_value = pairs_per_step * args.steps / (ms_e2e * 1e-3)
 
-    # dominant kernel, timed alone with CUDA events on the launch stream
+    # per-kernel device time of one step (CUPTI through torch.profiler: the three kernels of a block call run on two streams)
     roofline = None
     if rank == 0 and not args.no_profile_pass:
-        T.lib.start_timing()
-        step(0, False)
-        stats = T.lib.stop_timing()
-        calls, tot_ms = stats["topo_distance_block"]
-        flop = 6.0 * R * n * d_bins                       # P x D x 6 flop
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            step(0, False)
+            torch.cuda.synchronize()
+        kt = {}
+        for ev in prof.key_averages():
+            for name in ("gram_kernel", "l1_kernel", "combine_kernel", "distance_prepare_kernel"):
+                if name in ev.key:
+                    kt[name] = kt.get(name, 0.0) + ev.device_time_total / 1e3          # ms
         sm = torch.cuda.get_device_properties(dev).multi_processor_count
         mhz = (clocks or {}).get("sm_max_mhz") or 1965.0
-        peak = sm * FP32_FMA_LANES_PER_SM * 2 * mhz * 1e6 / 1e12
-        roofline = {"kernel": "topo_distance_block (distance_rows_kernel)", "bound": "fp32_alu", "unit": "TFLOP/s",
-                    "achieved": flop / (tot_ms * 1e-3) / 1e12, "peak": peak, "frac": flop / (tot_ms * 1e-3) / 1e12 / peak,
-                    "peak_source": f"nominal: {sm} SMs x 128 FP32 lanes x 2 flop x {mhz:.0f} MHz (no measured FP32 figure in MEASURED_PEAKS.json)",
-                    "traffic": None, "launches_per_step": calls, "kernel_ms_per_step": tot_ms,
-                    "share_of_step": tot_ms / (ms / args.steps),
-                    "note": "not HBM- or tensor-bound: 4 FP32 instructions per pair-element (FADD, FFMA, FADD, FADD|.|); the "
-                            "L1-of-logs term is not a GEMM. 6 flop per pair-element as SURVEY 8(d) counts them; "
-                            "instruction-issue fraction = frac x 4/3"}
+        pair_elems = float(R) * n * d_bins
+        l1_ms, gram_ms = kt.get("l1_kernel", 0.0), kt.get("gram_kernel", 0.0)
+        fp32_peak = sm * FP32_FMA_LANES_PER_SM * mhz * 1e6 / 1e12                       # T instructions / s
+        from bench import peaks as _peaks
+        roofline = {"kernel": "l1_kernel (FP32 pipe, L1-of-logs term)", "bound": "fp32_alu", "unit": "T FP32 instructions/s",
+                    "achieved": 2.0 * pair_elems / (l1_ms * 1e-3) / 1e12 if l1_ms else None, "peak": fp32_peak,
+                    "frac": (2.0 * pair_elems / (l1_ms * 1e-3) / 1e12 / fp32_peak) if l1_ms else None,
+                    "peak_source": f"nominal issue rate: {sm} SMs x 128 FP32 lanes x {mhz:.0f} MHz (MEASURED_PEAKS.json has no FP32 figure)",
+                    "traffic": None, "kernel_ms_per_step": kt, "share_of_step": l1_ms / (ms / args.steps),
+                    "algorithmic_instructions_per_pair_element": 2,
+                    "note": "2 FP32 instructions per pair-element (FADD, FADD|.|): not a GEMM, not HBM-bound (operands are re-read from L2)",
+                    "gram_kernel": {"bound": "tensor", "unit": "TFLOP/s (bf16, six part products per fp32 product)",
+                                    "achieved": 12.0 * pair_elems / (gram_ms * 1e-3) / 1e12 if gram_ms else None,
+                                    "peak": json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "MEASURED_PEAKS.json")))["bf16_tflops_sustained"]
+                                    if os.path.exists(os.path.join(os.path.dirname(os.path.abspath(__file__)), "MEASURED_PEAKS.json")) else 1400.0,
+                                    "operand_bytes_streamed": 2.0 * 6.0 * pair_elems / 128.0,
+                                    "note": "128 x 128 tiles: 96 KB of operand image per 64-bin chunk -> bound by L2 / HBM operand streaming, "
+                                            "not by the tensor pipe; it is ~1/4 of the step and overlaps nothing yet"}}
+        if roofline["gram_kernel"]["achieved"]:
+            roofline["gram_kernel"]["frac"] = roofline["gram_kernel"]["achieved"] / roofline["gram_kernel"]["peak"]
+            roofline["gram_kernel"]["operand_GBps"] = roofline["gram_kernel"]["operand_bytes_streamed"] / (gram_ms * 1e-3) / 1e9
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = _distance_cpu(args, pairs=24)

@@ -368,12 +368,37 @@ __global__ void __launch_bounds__(256) combine_kernel(DistOperand rows, DistOper
     out[i * ld_out + j] = (rows.g0 + li == cols.g0 + lj) ? 0.f : dist;
 }
 
+// The Gram kernel (tensor pipe + TMA engine, one CTA per SM for its 192 KB operand ring) and the L1 kernel (FP32 pipe) are
+// independent until the combine: they are launched on two streams that fork from and join the caller's, so the block
+// scheduler may run them side by side.  One side stream and two events per device, created on first use.
+struct SideStream {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+};
+SideStream* side_stream() {
+    static SideStream per_device[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    SideStream& ss = per_device[dev >= 0 && dev < 64 ? dev : 0];
+    if (ss.stream == nullptr) {
+        if (cudaStreamCreateWithFlags(&ss.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&ss.join, cudaEventDisableTiming);
+    }
+    return &ss;
+}
+
 int launch_distance(const DistOperand& rows, const DistOperand& cols, const Segments& seg, int64_t row_begin, int64_t row_end,
                     int64_t col_begin, int64_t col_end, float* workspace, float* out, int64_t ld_out, topo_stream_t stream) {
     const int64_t nr = row_end - row_begin, nc = col_end - col_begin;
     float* gram = workspace;
     float* l1 = workspace + static_cast<int64_t>(seg.n) * nr * nc;
-    cudaStream_t s = as_stream(stream);
+    cudaStream_t main_stream = as_stream(stream);
+    SideStream* ss = side_stream();
+    TOPO_REQUIRE(ss != nullptr, "could not create the side stream of the distance sweep");
+    TOPO_CUDA(cudaEventRecord(ss->fork, main_stream));
+    TOPO_CUDA(cudaStreamWaitEvent(ss->stream, ss->fork, 0));
+    cudaStream_t s = ss->stream;
     {
         const int64_t rt0 = row_begin / kRowsPerBlock, rt1 = (row_end + kRowsPerBlock - 1) / kRowsPerBlock;
         const int64_t ct0 = col_begin / kRowsPerBlock, ct1 = (col_end + kRowsPerBlock - 1) / kRowsPerBlock;
@@ -381,10 +406,13 @@ int launch_distance(const DistOperand& rows, const DistOperand& cols, const Segm
         const dim3 grid(static_cast<unsigned>(ct1 - ct0), static_cast<unsigned>(rt1 - rt0), static_cast<unsigned>(seg.n));
         gram_kernel<<<grid, kGramThreads, GramSmem::kTotal, s>>>(rows, cols, seg, rt0, ct0, nr, nc, row_begin, col_begin, gram);
     }
+    TOPO_CUDA(cudaEventRecord(ss->join, ss->stream));
+    s = main_stream;
     {
         const dim3 grid(static_cast<unsigned>((nc + TJ - 1) / TJ), static_cast<unsigned>((nr + TI - 1) / TI));
         l1_kernel<<<grid, 256, 0, s>>>(rows, cols, seg, row_begin, row_end, col_begin, col_end, l1);
     }
+    TOPO_CUDA(cudaStreamWaitEvent(main_stream, ss->join, 0));
     {
         const int64_t total = nr * nc;
         combine_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(rows, cols, seg, row_begin, nr, col_begin, nc, gram, l1,
