@@ -61,7 +61,7 @@ def parse_args():
                          "distance sweep (configs[4]); full_step: front-end + stage + decoder + loss + optimizer, data-parallel "
                          "(configs[3])")
     ap.add_argument("--clips", type=int, default=4096, help="distance: clips in the collection")
-    ap.add_argument("--row-block", type=int, default=512, help="distance: rows per GPU per step")
+    ap.add_argument("--row-block", type=int, default=1024, help="distance: rows per GPU per step")
     ap.add_argument("--top-k", type=int, default=32, help="distance: neighbours kept per row")
     ap.add_argument("--clip-samples", type=int, default=64000, help="distance: samples per clip (4 s at 16 kHz)")
     ap.add_argument("--micro-batches", type=int, default=4, help="full_step: accumulated micro-batches per optimizer step")

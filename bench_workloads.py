@@ -58,7 +58,7 @@ def run_distance(args):
     n, R, k = args.clips, args.row_block, args.top_k
     audio_h = _clips(n, args.clip_samples, SEED).pin_memory()       # identical collection on every rank
     # column spectra: prepared once when they fit (pd.spectral_topk does the same), in blocks of 512 clips
-    col_block = 2048          # one launch = row_block x 2048 pairs in 64 x 64 tiles: 128 CTAs per 256 rows, several per SM
+    col_block = 4096          # one launch = row_block x 4096 pairs: 128 x 64 L1 tiles -> 512 CTAs per 1024 rows, 3.5 per SM
     cols = [pd.prepare_block(audio_h[c0:c0 + col_block], dev) for c0 in range(0, n, col_block)]
     d_bins, dp = cols[0].d, cols[0].dp
     lo, hi = pd.shard_rows(n, rank, world)

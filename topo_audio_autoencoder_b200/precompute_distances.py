@@ -148,7 +148,7 @@ def prepare_block(audio_block: torch.Tensor, device, scales: Sequence[int] = SCA
 
 
 @torch.no_grad()
-def spectral_topk(audio: torch.Tensor, k: int, row_block: int = 1024, col_block: int = 2048, rank: int = 0,
+def spectral_topk(audio: torch.Tensor, k: int, row_block: int = 1024, col_block: int = 4096, rank: int = 0,
                   world_size: int = 1, device=None, scales: Sequence[int] = SCALES, cache_bytes: int = 48 << 30):
     """Streaming sweep for collections whose spectra do not fit in HBM (config 5: 100k clips x 2.58 MB x 2 arrays).
 
@@ -158,8 +158,9 @@ def spectral_topk(audio: torch.Tensor, k: int, row_block: int = 1024, col_block:
     row survive a block (running top-k merge), so nothing of size N x N is ever formed.  When all column spectra fit in
     `cache_bytes` they are prepared once instead.
 
-    Launch geometry: one launch reduces row_block x col_block pairs in 64 x 64 tiles, so the blocks are chosen large
-    enough for several CTAs per SM (1024 x 2048 = 512 tiles on 148 SMs); a row block of 1024 clips keeps 5.3 GB resident.
+    Launch geometry: one launch reduces row_block x col_block pairs in 128 x 64 (L1 term) and 128 x 128 x 5 scales (Gram
+    term) tiles, so the blocks are chosen large enough for several CTAs per SM (1024 x 4096: 512 and 1280 CTAs on 148 SMs);
+    a row block of 1024 clips keeps 6.7 GB resident, a column block of 4096 clips 27 GB.
 
     -> (distances [rows, k] ascending, neighbour indices [rows, k] int64, collection-wide; self excluded,
         reference :121-126), on `device`."""
