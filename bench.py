@@ -451,6 +451,41 @@ def run_ours(args):
                           "bytes_per_sample": stage_bytes, "frac_of_nominal_8TBs": ach / 8000.0, "per": "GPU",
                           "note": "SURVEY.md 8(d) algorithmic bytes per sample x samples/s per GPU"}
 
+    # ---- per-call latency at the reference's own batch size (trainer.py:93 trains with batch size 1) ----
+    latency = None
+    if rank == 0 and world == 1 and not args.no_profile_pass and not args.no_graph:
+        from topo_audio_autoencoder_b200.graph import GraphedStep
+        latency = {"unit": "ms per forward+backward call, device time", "what": "same stage and weights, smaller batches"}
+        for small in (1, 8):
+            lg_s, nz_s = synthetic_inputs(small, n_total, args.regime, 1000 + small)
+            lg_s, nz_s = lg_s.to(dev), nz_s.to(dev)
+            ups_s = [u[:small * c] for u, c in zip(ups, counts_max)] + [ones[:small], ones[:small]]
+            gs = GraphedStep(stage, lg_s, nz_s, ups_s)
+
+            def eager_small():
+                for p_ in params:
+                    p_.grad = None
+                l_ = lg_s.detach().requires_grad_(True)
+                o_ = stage(l_, nz_s)
+                torch.autograd.backward([o_[f"rank_{r}"] for r in range(4)] + [o_["vertex_penalty"], o_["entropy_loss"]], ups_s)
+
+            res = {}
+            for name, fn, reps in (("cuda_graph_replay", lambda: gs.replay(lg_s, nz_s), 20), ("eager_python_launches", eager_small, 5)):
+                for _ in range(2):
+                    fn()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(reps):
+                    fn()
+                e1.record()
+                torch.cuda.synchronize()
+                res[name] = e0.elapsed_time(e1) / reps
+            latency[f"B={small}"] = res
+            del gs
+        if graphed is not None:      # the small captures recalibrated the SM split estimate: restore the benchmarked batch's
+            stage.calibrate(logits_d, noise_d)
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:      # at N > 1 the other ranks would idle in the final barrier
         torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
@@ -475,7 +510,7 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": (2 * B + 1) * 4,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "roofline_stage": roofline_stage,
-            "cpu_baseline": cpu, "breakdown": breakdown,
+            "cpu_baseline": cpu, "latency": latency, "breakdown": breakdown,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -433,6 +433,17 @@ class _LayerCombineFn(torch.autograd.Function):
             for pr, gx in zip(per, g_x):
                 pr["g_x_total"] = gx
             tail.join()
+        # The three message scales are shared by all ranks of the layer: autograd would add up one 1-element gradient per
+        # (rank, message) -- seven tiny launches per layer in the middle of the backward chain.  One product with a 0/1
+        # matrix sums them per distinct scale; the total is handed to the scale's first occurrence, the others get None.
+        owners, groups = [], {}
+        for pr, rc in zip(per, ranks):
+            for k in range(rc["n_msgs"]):
+                key = pr["scales"][k].data_ptr()
+                owners.append(groups.setdefault(key, len(groups)))
+        onehot = _scale_groups(tuple(owners), len(groups), dev)
+        g_s_tot = g_s_all @ onehot                                   # [distinct scales]
+        handed = set()
         n_agg = 0 if agg is not None else 1
         q = 0
         for i, (pr, rc) in enumerate(zip(per, ranks)):
@@ -448,9 +459,26 @@ class _LayerCombineFn(torch.autograd.Function):
                 if n_agg:
                     grads_flat[first + 7 + k] = pr["g_aggs"][k]
                 grads_flat[first + 7 + n * n_agg + k] = g_w_all[q]
-                grads_flat[first + 7 + n * (n_agg + 1) + k] = g_s_all[q:q + 1].reshape(pr["scales"][k].shape)
+                grp = owners[q]
+                if grp not in handed:
+                    handed.add(grp)
+                    grads_flat[first + 7 + n * (n_agg + 1) + k] = g_s_tot[grp:grp + 1].reshape(pr["scales"][k].shape)
                 q += 1
         return (None, *grads_flat)
+
+
+_SCALE_GROUPS: Dict[tuple, torch.Tensor] = {}
+
+
+def _scale_groups(owners: tuple, n_groups: int, device) -> torch.Tensor:
+    """[len(owners), n_groups] 0/1 matrix: entry (q, g) = message q uses distinct scale g (cached per device and pattern)."""
+    key = (owners, n_groups, str(device))
+    if key not in _SCALE_GROUPS:
+        m = torch.zeros(len(owners), n_groups, dtype=torch.float32)
+        for q, g in enumerate(owners):
+            m[q, g] = 1.0
+        _SCALE_GROUPS[key] = m.to(device)
+    return _SCALE_GROUPS[key]
 
 
 def _make_params(ch, n_msgs, aggs, ws, scales, x, tensors, ln_eps, apply_ln, saved=None, tile_fragment=False,
