@@ -123,3 +123,27 @@ def test_gram_term_keeps_fp32_accuracy_for_near_duplicates():
     assert mine[:2].abs().max().item() < 5e-6, mine[:2]
     assert_close("distance/near-duplicates", mine[2:], want[2:], rtol=2e-5, atol=3e-6)
     assert (got >= 0).all()
+
+
+def test_edge_sizes_of_the_sweep():
+    """one clip, two clips, k larger than the collection, block sizes that do not divide anything, short clips"""
+    from topo_audio_autoencoder_b200 import precompute_distances as pd
+    g = torch.Generator().manual_seed(5)
+    one = torch.randn(1, 1, 3000, generator=g) * 0.1
+    d1 = pd.pairwise_spectral_distances(one.cuda())
+    assert tuple(d1.shape) == (1, 1) and d1.item() == 0.0
+    v, i = pd.spectral_topk(one.cuda(), 4)
+    assert tuple(v.shape) == (1, 0) and tuple(i.shape) == (1, 0)
+    audio = torch.randn(131, 1, 2500, generator=g) * 0.1          # 131 clips: two 128-clip image blocks, the second nearly empty
+    dense = pd.pairwise_spectral_distances(audio.cuda())
+    want = do.pairwise_matrix(audio[:9], batch_size=4)
+    assert_close("distance/edge/131-clips", dense[:9, :9], want, rtol=2e-5, atol=2e-6)
+    assert torch.isfinite(dense).all() and torch.equal(dense, dense.t())
+    v, i = pd.spectral_topk(audio.cuda(), 500, row_block=50, col_block=77)      # k clamps to n - 1
+    assert tuple(v.shape) == (131, 130)
+    wv, wi = pd.neighbour_order(dense)
+    assert_close("distance/edge/full-order", v, wv, rtol=2e-6, atol=1e-6)
+    assert (torch.sort(i, dim=1).values == torch.sort(wi, dim=1).values).all(), "every other clip exactly once"
+    two = audio[:2].cuda()
+    d2 = pd.pairwise_spectral_distances(two)
+    assert_close("distance/edge/two", d2[0, 1].reshape(1), do.batch_audio_distance(audio[:1], audio[1:2]), rtol=2e-5, atol=2e-6)
