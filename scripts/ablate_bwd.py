@@ -1,13 +1,13 @@
 """GPU: in-kernel timeline (globaltimer) of the fused backward at the rank-3 size."""
-# needs a debug build of the library:  TOPO_DEBUG_KERNELS=1 python topo_audio_autoencoder_b200/csrc/build.py --force
+# runs on libtopo_b200_debug.so (csrc/build.py builds it next to the product library): the hooks do not exist in the product
 import ctypes as C
 import sys
 import torch
 sys.path.insert(0, ".")
-from topo_audio_autoencoder_b200._lib import lib, check, ptr, stream, CombineGrads  # noqa: E402
+from topo_audio_autoencoder_b200._lib import load_debug, check, ptr, stream, CombineGrads  # noqa: E402
 from topo_audio_autoencoder_b200.custom_sccn import _make_params  # noqa: E402
 
-raw = lib._cdll
+raw = lib = load_debug()          # kernels AND hooks from the debug twin (the hooks set globals of that library)
 raw.topo_debug_bwd_stamps.argtypes = [C.c_void_p]
 raw.topo_debug_bwd_stamps.restype = None
 rows, ch, n_msgs = 310080, 64, 2
