@@ -493,7 +493,7 @@ __global__ void __launch_bounds__(kThreads, V == 1 ? 8 : 5) agg_same_bwd(const D
     Group<L, V> g;
     int r, row, id;
     long long axis;
-    if (!locate<L, V, false>(d, sec, cv, &g, &r, &row, &id, &axis)) return;
+    if (!locate<L, V, true>(d, sec, cv, &g, &r, &row, &id, &axis)) return;
     switch (r) {
         case 0: same_bwd_body<L, V, 0>(d, g, row, id, axis, x, down, up, g_same, g_down, g_up, g_x, g_probs); break;
         case 1: same_bwd_body<L, V, 1>(d, g, row, id, axis, x, down, up, g_same, g_down, g_up, g_x, g_probs); break;
@@ -562,7 +562,7 @@ __global__ void __launch_bounds__(kThreads) agg_cross_bwd(const DeviceTables d, 
     Group<L, V> g;
     int r, row, id;
     long long axis;
-    if (!locate<L, V, false>(d, sec, cv, &g, &r, &row, &id, &axis)) return;
+    if (!locate<L, V, true>(d, sec, cv, &g, &r, &row, &id, &axis)) return;
     switch (r) {
         case 0: cross_bwd_body<L, V, 0>(d, g, row, id, axis, x, g_down, g_up, g_x, g_probs); break;
         case 1: cross_bwd_body<L, V, 1>(d, g, row, id, axis, x, g_down, g_up, g_x, g_probs); break;
@@ -585,7 +585,7 @@ __global__ void __launch_bounds__(kThreads, 4) agg_top_bwd(const DeviceTables d,
     Group<L, V> g;
     int r, row, id;
     long long axis;
-    if (!locate<L, V, false>(d, sec, cv, &g, &r, &row, &id, &axis, sec.begin[3])) return;
+    if (!locate<L, V, true>(d, sec, cv, &g, &r, &row, &id, &axis, sec.begin[3])) return;
     using F = FV<V>;
     const float p = g.probs[d.off[3] + id];
     int fr[4];
