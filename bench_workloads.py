@@ -16,7 +16,7 @@ import torch
 
 from bench import SEED, ClockSampler, peaks
 
-FP32_FMA_LANES_PER_SM = 128
+INT_LANES_PER_SM = 64          # VABSDIFF: one warp instruction per two clocks and SM sub-partition (scripts/probes/sad_rate.cu)
 
 
 def _dist_env():
@@ -145,15 +145,16 @@ def run_distance(args):
         mhz = (clocks or {}).get("sm_max_mhz") or 1965.0
         pair_elems = float(R) * n * d_bins
         l1_ms, gram_ms = kt.get("l1_kernel", 0.0), kt.get("gram_kernel", 0.0)
-        fp32_peak = sm * FP32_FMA_LANES_PER_SM * mhz * 1e6 / 1e12                       # T instructions / s
-        from bench import peaks as _peaks
-        roofline = {"kernel": "l1_kernel (FP32 pipe, L1-of-logs term)", "bound": "fp32_alu", "unit": "T FP32 instructions/s",
-                    "achieved": 2.0 * pair_elems / (l1_ms * 1e-3) / 1e12 if l1_ms else None, "peak": fp32_peak,
-                    "frac": (2.0 * pair_elems / (l1_ms * 1e-3) / 1e12 / fp32_peak) if l1_ms else None,
-                    "peak_source": f"nominal issue rate: {sm} SMs x 128 FP32 lanes x {mhz:.0f} MHz (MEASURED_PEAKS.json has no FP32 figure)",
+        int_peak = sm * INT_LANES_PER_SM * mhz * 1e6 / 1e12                             # T instructions / s
+        roofline = {"kernel": "l1_kernel (integer pipe, L1-of-logs term)", "bound": "int_alu", "unit": "T integer instructions/s",
+                    "achieved": pair_elems / (l1_ms * 1e-3) / 1e12 if l1_ms else None, "peak": int_peak,
+                    "frac": (pair_elems / (l1_ms * 1e-3) / 1e12 / int_peak) if l1_ms else None,
+                    "peak_source": f"nominal issue rate of the integer pipe: {sm} SMs x 64 lanes x {mhz:.0f} MHz (MEASURED_PEAKS.json has "
+                                   "no ALU figure; scripts/probes/sad_rate.cu measured 62.2 of the 64 per clock and SM)",
                     "traffic": None, "kernel_ms_per_step": kt, "share_of_step": l1_ms / (ms / args.steps),
-                    "algorithmic_instructions_per_pair_element": 2,
-                    "note": "2 FP32 instructions per pair-element (FADD, FADD|.|): not a GEMM, not HBM-bound (operands are re-read from L2)",
+                    "algorithmic_instructions_per_pair_element": 1,
+                    "note": "1 integer instruction per pair-element (VABSDIFF.U32 with accumulate on Q6.20 logs; the FP32 form needs 2: "
+                            "FADD, FADD|.|): not a GEMM, not HBM-bound (operands are re-read from L2 by the TMA engine)",
                     "gram_kernel": {"bound": "tensor", "unit": "TFLOP/s (bf16, six part products per fp32 product)",
                                     "achieved": 12.0 * pair_elems / (gram_ms * 1e-3) / 1e12 if gram_ms else None,
                                     "peak": json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "MEASURED_PEAKS.json")))["bf16_tflops_sustained"]

@@ -376,22 +376,27 @@ void topo_debug_bwd_stamps(unsigned long long* device_buffer);
  *   d(i,j) = sum_s [ mean((x_s-y_s)^2) / (mean(x_s^2) + 1e-7) + mean|log(x_s+eps) - log(y_s+eps)| ]
  * with x = the LOWER-index clip (so the normaliser comes from it, :89, :106-110), mirrored
  * (:114-115), zero diagonal.  The squared-difference term is evaluated as mean x^2 + mean y^2 - 2 <x, y> / len with the
- * Gram term <x, y> on the tensor cores (bf16x3, fp32-accurate, two-level accumulation); the L1-of-logs term on the FP32 pipe.
+ * Gram term <x, y> on the tensor cores (bf16x3, fp32-accurate, two-level accumulation); the L1-of-logs term on the integer
+ * pipe (one VABSDIFF per pair-element) from Q6.20 fixed-point logs q(v) = round((v + 40) 2^20): exact for |v| >= 8, 9.5e-7
+ * resolution below, window [-40, 24) in log units (log_eps >= 1e-17, magnitudes below 2.6e10; values outside saturate).
  *   padded_size     : row length Dp after every segment is padded to a multiple of 64 bins
  *   image_bytes     : size of the bf16x3 operand image of n clips ([ceil(n / 128)][Dp / 64] tiles of 48 KB)
+ *   logq_words      : 32-bit words of the fixed-point log operand of n clips ([ceil(n / 64)][Dp][64], k-major inside
+ *                     64-clip blocks so that a stage of the L1 kernel is three contiguous 8 KB pieces)
  *   workspace_floats: scratch of one rows / block call (Gram and L1 partials per scale)
- *   prepare         : spec -> logspec_p [n, Dp] = log(spec + eps) (0 in the padding), image (1024-byte aligned; rows past n
- *                     in the last 128-clip block must be zero: allocate it zero-filled), sq_mean [n, n_scales]
+ *   prepare         : spec -> logq (16-byte aligned), image (1024-byte aligned; rows past n in the last 128-clip block must
+ *                     be zero: allocate it zero-filled), sq_mean [n, n_scales]
  *   rows            : the block [row_begin, row_end) x [col_begin, col_end) of the symmetric matrix of ONE prepared set
  *                     (row-block sharding across ranks needs no collective)
  * ------------------------------------------------------------------------------------------- */
 int64_t topo_distance_padded_size(const int64_t* host_seg_len, int n_scales);
 int64_t topo_distance_image_bytes(int64_t n, const int64_t* host_seg_len, int n_scales);
+int64_t topo_distance_logq_words(int64_t n, const int64_t* host_seg_len, int n_scales);
 int64_t topo_distance_workspace_floats(int64_t n_rows, int64_t n_cols, int n_scales);
 int topo_distance_prepare(const float* spec, int64_t n, int64_t d, const int64_t* host_seg_len,
-                          int n_scales, float log_eps, float* logspec_p, void* image,
+                          int n_scales, float log_eps, uint32_t* logq, void* image,
                           float* sq_mean, topo_stream_t stream);
-int topo_distance_rows(const float* logspec_p, const void* image, const float* sq_mean, int64_t n,
+int topo_distance_rows(const uint32_t* logq, const void* image, const float* sq_mean, int64_t n,
                        const int64_t* host_seg_len, int n_scales, int64_t row_begin, int64_t row_end,
                        int64_t col_begin, int64_t col_end, float* workspace, float* out, topo_stream_t stream);
 
@@ -400,8 +405,8 @@ int topo_distance_rows(const float* logspec_p, const void* image, const float* s
  * in HBM).  row_* hold clips [row_global0, row_global0 + n_rows) of the collection, col_* clips [col_global0, ...); the
  * collection-wide indices decide which clip of a pair is the lower one (its mean square is the normaliser, :106-110) and
  * where the diagonal is.  out[i * ld_out + j], i < n_rows, j < n_cols. */
-int topo_distance_block(const float* row_logspec, const void* row_image, const float* row_sq_mean, int64_t n_rows,
-                        int64_t row_global0, const float* col_logspec, const void* col_image, const float* col_sq_mean,
+int topo_distance_block(const uint32_t* row_logq, const void* row_image, const float* row_sq_mean, int64_t n_rows,
+                        int64_t row_global0, const uint32_t* col_logq, const void* col_image, const float* col_sq_mean,
                         int64_t n_cols, int64_t col_global0, const int64_t* seg_len, int n_scales, float* workspace,
                         float* out, int64_t ld_out, topo_stream_t stream);
 

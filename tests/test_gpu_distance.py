@@ -147,3 +147,36 @@ def test_edge_sizes_of_the_sweep():
     two = audio[:2].cuda()
     d2 = pd.pairwise_spectral_distances(two)
     assert_close("distance/edge/two", d2[0, 1].reshape(1), do.batch_audio_distance(audio[:1], audio[1:2]), rtol=2e-5, atol=2e-6)
+
+
+def test_fixed_point_logs_cover_silence_and_loud_clips():
+    """The L1 term runs on Q6.20 fixed-point logs (window [-40, 24) in log units, csrc/distance.cu): digital silence
+    (log(1e-7) = -16.1 in every bin), very quiet, ordinary and very loud clips against the fp32 oracle, and the L1 term on
+    its own against an fp64 sum of the same fp32 logs."""
+    from topo_audio_autoencoder_b200 import precompute_distances as pd
+    g = torch.Generator().manual_seed(77)
+    base = torch.randn(4, 1, 16000, generator=g) * 0.1
+    audio = torch.cat([torch.zeros(1, 1, 16000), base[:1] * 1e-4, base[1:2], base[2:3] * 1e3, base[3:4] * 3e4])
+    got = pd.pairwise_spectral_distances(audio.cuda()).cpu()
+    want = do.pairwise_matrix(audio, batch_size=4)
+    assert_close("distance/fixed-point-window", got, want, rtol=2e-5, atol=2e-6)
+    # the L1 term alone: d(i, j) - relative-L2 term, both sides from the same spectra
+    spec, seg = pd.multiscale_spectrograms(audio.cuda())
+    logs = torch.log(spec.double() + pd.LOG_EPSILON)
+    assert logs.min().item() > -40 and logs.max().item() < 24
+    off = 0
+    l1 = torch.zeros(5, 5, dtype=torch.float64, device="cuda")
+    l2 = torch.zeros(5, 5, dtype=torch.float64, device="cuda")
+    for n_s in seg:
+        x, lx = spec[:, off:off + n_s].double(), logs[:, off:off + n_s].float().double()
+        l1 += (lx[:, None, :] - lx[None, :, :]).abs().mean(-1)
+        msq = ((x[:, None, :] - x[None, :, :]) ** 2).mean(-1)
+        norm = (x ** 2).mean(-1)
+        idx = torch.arange(5, device="cuda")
+        l2 += msq / (torch.where(idx[:, None] <= idx[None, :], norm[:, None], norm[None, :]) + 1e-7)      # the lower-index clip's
+        off += n_s
+    ref = (l1 + l2).float().cpu()
+    ref.fill_diagonal_(0)
+    assert_close("distance/fixed-point-vs-fp64", got, ref, rtol=5e-6, atol=2e-6)
+    with pytest.raises(RuntimeError, match="fixed-point window"):
+        pd.PreparedSpectra(spec, seg, log_eps=1e-20)

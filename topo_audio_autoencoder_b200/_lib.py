@@ -105,6 +105,7 @@ SIGNATURES = {
     "topo_sccn_combine_bwd_tc": [C.POINTER(CombineParams), _I64, _P, _P, C.POINTER(CombineGrads), _P],
     "topo_distance_padded_size": [C.POINTER(_I64), _I32],
     "topo_distance_image_bytes": [_I64, C.POINTER(_I64), _I32],
+    "topo_distance_logq_words": [_I64, C.POINTER(_I64), _I32],
     "topo_distance_workspace_floats": [_I64, _I64, _I32],
     "topo_distance_prepare": [_P, _I64, _I64, C.POINTER(_I64), _I32, _F, _P, _P, _P, _P],
     "topo_distance_rows": [_P, _P, _P, _I64, C.POINTER(_I64), _I32, _I64, _I64, _I64, _I64, _P, _P, _P],
@@ -113,7 +114,7 @@ SIGNATURES = {
 _NON_STATUS = {"topo_version": C.c_int, "topo_last_error": C.c_char_p, "topo_tables_destroy": None,
                "topo_debug_fwd16_mask": None, "topo_debug_fwd16_stamps": None, "topo_debug_bwd_stamps": None,
                "topo_distance_padded_size": C.c_int64, "topo_distance_image_bytes": C.c_int64,
-               "topo_distance_workspace_floats": C.c_int64}
+               "topo_distance_workspace_floats": C.c_int64, "topo_distance_logq_words": C.c_int64}
 
 # unit-test / measurement entry points: only in libtopo_b200_debug.so (csrc/build.py build_debug()), never in the product library
 DEBUG_LIB_PATH = os.path.join(_HERE, "libtopo_b200_debug.so")
@@ -159,7 +160,7 @@ KERNELS_PER_CALL = {
     "topo_embed_bwd": 2, "topo_layernorm_fwd": 1, "topo_layernorm_bwd": 1, "topo_operators_count": 2,
     "topo_operators_fill": 1, "topo_operators_bwd": 1, "topo_sccn_aggregate_fwd": 2, "topo_sccn_aggregate_bwd": 3,
     "topo_spmm_csr": 1, "topo_sddmm_csr": 1, "topo_sccn_prepare_images": 1, "topo_sccn_finish_weight_grads": 1, "topo_sccn_combine_fwd": 1, "topo_sccn_combine_fwd_tc": 1, "topo_sccn_combine_fwd_tc2": 1, "topo_sccn_combine_bwd": 2,
-    "topo_sccn_combine_bwd_attention": 1, "topo_sccn_combine_bwd_conv": 1, "topo_sccn_combine_bwd_conv_tc": 1, "topo_sccn_combine_bwd_tc": 1, "topo_distance_prepare": 1,
+    "topo_sccn_combine_bwd_attention": 1, "topo_sccn_combine_bwd_conv": 1, "topo_sccn_combine_bwd_conv_tc": 1, "topo_sccn_combine_bwd_tc": 1, "topo_distance_prepare": 2,
     "topo_distance_rows": 3, "topo_distance_block": 3,
 }
 

@@ -13,8 +13,9 @@
 //     issues tcgen05.mma into a ping-pong pair of tensor-memory accumulators, eight warps drain them.  Accumulation is
 //     two-level so that a 130,000-term sum keeps fp32 accuracy: tensor memory holds 64 terms, registers 32 x 64,
 //     the output tile the rest.
-//   * L1 of logs:  sum |log x - log y| is not a GEMM -- `l1_kernel`: 2 FP32 instructions per pair-element on a 128 x 64
-//     pair tile, operands staged k-major through shared memory so one LDS.128 feeds four pairs, two-level sums.
+//   * L1 of logs:  sum |log x - log y| is not a GEMM -- `l1_kernel`: ONE integer instruction per pair-element (VABSDIFF with
+//     accumulate) on Q6.20 fixed-point logs, 128 x 64 pair tile, operands pre-transposed in global memory (`logq`) so that a
+//     stage of 32 bins is three contiguous 8 KB pieces the TMA engine drops into a four-stage shared-memory ring.
 //   * `combine_kernel` folds both per scale with the lower-index clip's normaliser.
 #include <algorithm>
 
@@ -59,17 +60,15 @@ Segments make_segments(const int64_t* seg_len, int n_scales) {
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// prepare: one CTA per (clip, scale).  log(x + eps) padded row, mean of squares, and the bf16x3 image of the clip's row
-// inside its 128-clip block: image[block][k_chunk][part][row][64 bf16], rows swizzled exactly as tcgen05 wants them in
-// shared memory, so that a (block, k_chunk) operand tile is 48 contiguous kilobytes.
+// prepare: one CTA per (clip, scale).  Mean of squares and the bf16x3 image of the clip's row inside its 128-clip block:
+// image[block][k_chunk][part][row][64 bf16], rows swizzled exactly as tcgen05 wants them in shared memory, so that a
+// (block, k_chunk) operand tile is 48 contiguous kilobytes.
 // ------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) distance_prepare_kernel(const float* __restrict__ spec, long long d, Segments seg,
-                                                               float log_eps, float* __restrict__ logspec_p,
                                                                uint8_t* __restrict__ image, float* __restrict__ sq_mean) {
     const long long clip = blockIdx.x;
     const int s = blockIdx.y;
     const float* src = spec + clip * d + seg.src_off[s];
-    float* ldst = logspec_p + clip * seg.dp + seg.pad_off[s];
     const long long n_chunks = seg.dp / kChunk;
     const long long blk = clip / kRowsPerBlock;
     const int row = static_cast<int>(clip % kRowsPerBlock);
@@ -81,8 +80,7 @@ __global__ void __launch_bounds__(256) distance_prepare_kernel(const float* __re
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
             const long long k = k8 * 8 + e;
-            v[e] = k < seg.len[s] ? src[k] : 0.f;
-            ldst[k] = k < seg.len[s] ? logf(v[e] + log_eps) : 0.f;   // padding: 0 in both arrays, contributes to neither sum
+            v[e] = k < seg.len[s] ? src[k] : 0.f;                     // padding: 0, contributes to neither sum
             acc = fmaf(v[e], v[e], acc);
         }
         const long long kk = seg.pad_off[s] + k8 * 8;                 // position in the padded row
@@ -99,10 +97,50 @@ __global__ void __launch_bounds__(256) distance_prepare_kernel(const float* __re
     }
 }
 
+// The L1 term's operand: log(x + eps) as unsigned Q6.20 fixed point,
+//     q(v) = round((v + 40) * 2^20), clamped to [0, 2^26)          window [-40, 24): magnitudes from 4e-18 to 2.6e10
+// stored k-major inside 64-clip blocks, logq[clip / 64][padded bin][clip % 64], so that the 64 clips x 32 bins one stage of
+// `l1_kernel` consumes are 8 contiguous kilobytes.  q is exact for every fp32 value with |v| >= 8 and rounds to 2^-20 =
+// 9.5e-7 (one fp32 ulp of the values in [8, 16)) below; the rounding is unbiased and averages over the >= 129,000 bins of a
+// scale to ~1e-9 of the mean.  One CTA per (64-bin chunk, 64-clip block): coalesced reads along the bins, a transposition
+// through shared memory, coalesced 256-byte rows out.  Padding bins and the clips past n in the last block hold q(0).
+constexpr float kFixOffset = 40.0f, kFixScale = 1048576.0f, kFixMax = 67108863.0f;     // Q6.20
+constexpr int kQBlock = 64;           // clips per block of logq
+
+__device__ __forceinline__ uint32_t to_fixed(float v) {
+    return __float2uint_rn(fminf(fmaf(v, kFixScale, kFixOffset * kFixScale), kFixMax));   // negative and NaN saturate to 0
+}
+
+__global__ void __launch_bounds__(256) distance_logq_kernel(const float* __restrict__ spec, long long n, long long d, Segments seg,
+                                                            float log_eps, uint32_t* __restrict__ logq) {
+    __shared__ uint32_t tile[kChunk][kQBlock + 1];
+    const long long kp0 = static_cast<long long>(blockIdx.x) * kChunk;      // padded bin of this chunk (inside ONE scale)
+    const long long blk = blockIdx.y;
+    int s = 0;
+    while (s + 1 < seg.n && kp0 >= seg.pad_off[s + 1]) ++s;
+    const long long k_in_seg = kp0 - seg.pad_off[s] + (threadIdx.x & 63);
+    const bool k_ok = k_in_seg < seg.len[s];
+    const float* src = spec + seg.src_off[s] + k_in_seg;
+#pragma unroll 4
+    for (int i = 0; i < 16; ++i) {
+        const int c = (threadIdx.x >> 6) + 4 * i;
+        const long long clip = blk * kQBlock + c;
+        const float v = (k_ok && clip < n) ? logf(__ldg(src + clip * d) + log_eps) : 0.f;
+        tile[threadIdx.x & 63][c] = to_fixed(v);
+    }
+    __syncthreads();
+    uint32_t* dst = logq + (blk * seg.dp + kp0) * kQBlock;
+#pragma unroll 4
+    for (int i = 0; i < 16; ++i) {
+        const int k = (threadIdx.x >> 6) + 4 * i;
+        dst[k * kQBlock + (threadIdx.x & 63)] = tile[k][threadIdx.x & 63];
+    }
+}
+
 // Rows and columns may come from DIFFERENT prepared blocks (streaming sweep: a resident row block against column blocks
 // prepared on the fly): an operand holds clips [g0, g0 + count) of the collection.
 struct DistOperand {
-    const float* logspec;   // [count, dp]
+    const uint32_t* logq;   // [ceil(count / 64)][dp][64] Q6.20 logs
     const uint8_t* image;   // [ceil(count / 128)][dp / 64] chunks of 48 KB
     const float* sq_mean;   // [count, n_scales]
     long long count;        // clips in this block
@@ -248,99 +286,126 @@ __global__ void __launch_bounds__(kGramThreads, 1) gram_kernel(DistOperand rows,
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// L1 of logs on the FP32 pipe: 128 x 64 pair tile, 256 threads, thread (ty, tx) = (tid / 16, tid % 16) owns rows
-// 8 ty .. +7 and columns 4 tx .. +3.  l1[scale][i][j] = sum_k |lx_ik - ly_jk| (not yet divided by the segment length).
+// L1 of logs: grid = (64-clip column blocks, 128-clip row tiles, scales); a CTA reduces the 128 x 64 pair tile of one scale,
+// l1[scale][i][j] = sum_k |lx_ik - ly_jk| (not yet divided by the segment length).
+//
+// sum |a - b| costs two FP32 instructions per pair-element (FADD, FADD with |.|) and one on the integer pipe: VABSDIFF.U32
+// d = |a - b| + c on the fixed-point logs.  Measured on one B200 (scripts/probes/sad_rate.cu, operands from shared memory,
+// 8 x 4 pairs per thread): 54.5 pair-elements per clock and SM with FADDs, 62.2 with VABSDIFF (the integer pipe runs at half
+// the FADD rate but needs half the instructions); in this kernel the integer form also removes the accumulators' second
+// level, and it makes the sum exact inside a 64-bin chunk and independent of where a pair sits in its tile.
+//   warp 8, lane 0   producer: per stage of 32 bins three cp.async.bulk copies of 8 KB (row blocks 2t and 2t + 1, the
+//                    column block) into a four-stage ring, armed with mbarrier transaction counts
+//   warps 0..7       thread (ty, tx) = (tid / 16, tid % 16) owns rows 8 ty .. +7 and columns 4 tx .. +3: three LDS.128 and
+//                    32 VABSDIFF per bin; 64 differences of 26 bits fit a 32-bit accumulator exactly (segments are padded
+//                    to 64 bins), which is then added to the pair's fp32 sum; one mbarrier arrival per warp frees the stage
+// No thread touches a global operand, no __syncthreads in the loop.
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int TI = 128, TJ = 64;
-constexpr int LDI = TI + 4, LDJ = TJ + 4;
+constexpr int kL1KC = 32;                                   // bins per stage
+constexpr int kL1Stages = 4;
+constexpr int kL1Threads = 288;
+constexpr uint32_t kL1Piece = kL1KC * kQBlock * 4;          // 8 KB: [32 bins][64 clips]
+static_assert(kChunk % kL1KC == 0, "a 64-bin chunk is a whole number of stages");
 
-struct L1Stage {
-    float lx[KC * LDI];
-    float ly[KC * LDJ];
+struct L1Smem {
+    static constexpr uint32_t kStage = 3 * kL1Piece;        // row block 2t, row block 2t + 1, column block
+    static constexpr uint32_t kBar = kL1Stages * kStage;    // full[4], empty[4]
+    static constexpr uint32_t kTotal = kBar + 64;
 };
 
-__global__ void __launch_bounds__(256) l1_kernel(DistOperand rows, DistOperand cols, Segments seg, long long row_begin,
-                                                 long long row_end, long long col_begin, long long col_end,
-                                                 float* __restrict__ l1_out /* [scales][rows][cols] */) {
-    __shared__ __align__(16) L1Stage st[2];
-    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-    const long long i0 = row_begin + static_cast<long long>(blockIdx.y) * TI;
-    const long long j0 = col_begin + static_cast<long long>(blockIdx.x) * TJ;
-    const long long n_rows_out = row_end - row_begin, n_cols_out = col_end - col_begin;
+__global__ void __launch_bounds__(kL1Threads, 2) l1_kernel(DistOperand rows, DistOperand cols, Segments seg, long long row_tile0,
+                                                           long long col_block0, long long row_begin, long long row_end,
+                                                           long long col_begin, long long col_end,
+                                                           float* __restrict__ l1_out /* [scales][rows][cols] */) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + L1Smem::kBar);
+    uint64_t* empty = full + kL1Stages;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int s = blockIdx.z;
+    const long long rt = row_tile0 + blockIdx.y, cb = col_block0 + blockIdx.x;
+    const long long stages = seg.pad_len[s] / kL1KC;            // even: the segments are padded to 64 bins
 
-    // loader role: 4 threads per row fetch 16 consecutive bins (one float4 each); rows tid / 4 and tid / 4 + 64 of the
-    // row tile, row tid / 4 of the column tile
-    const int l_row = tid >> 2, l_k = (tid & 3) * 4;
-    const float* px0 = rows.logspec + min(i0 + l_row, rows.count - 1) * seg.dp + l_k;
-    const float* px1 = rows.logspec + min(i0 + l_row + 64, rows.count - 1) * seg.dp + l_k;
-    const float* py = cols.logspec + min(j0 + l_row, cols.count - 1) * seg.dp + l_k;
-    float4 r[3];
-    auto fetch = [&](long long k0) {
-        r[0] = __ldg(reinterpret_cast<const float4*>(px0 + k0));
-        r[1] = __ldg(reinterpret_cast<const float4*>(px1 + k0));
-        r[2] = __ldg(reinterpret_cast<const float4*>(py + k0));
-    };
-    auto scatter = [&](float* b, int ld, int row, const float4& v) {
-        b[(l_k + 0) * ld + row] = v.x;
-        b[(l_k + 1) * ld + row] = v.y;
-        b[(l_k + 2) * ld + row] = v.z;
-        b[(l_k + 3) * ld + row] = v.w;
-    };
-    auto deposit = [&](L1Stage& s) {
-        scatter(s.lx, LDI, l_row, r[0]);
-        scatter(s.lx, LDI, l_row + 64, r[1]);
-        scatter(s.ly, LDJ, l_row, r[2]);
-    };
-
-    const long long stages_total = seg.dp / KC;
-    fetch(0);
-    deposit(st[0]);
-    __syncthreads();
-    long long g = 0;
-    for (int s = 0; s < seg.n; ++s) {
-        float l1[8][4];
-#pragma unroll
-        for (int a = 0; a < 8; ++a)
-#pragma unroll
-            for (int c = 0; c < 4; ++c) l1[a][c] = 0.f;
-        const long long stages = seg.pad_len[s] / KC;
-        for (long long q = 0; q < stages; ++q, ++g) {
-            const L1Stage& cur = st[g & 1];
-            const bool more = (g + 1) < stages_total;
-            if (more) fetch((g + 1) * KC);
-            float l1_i[8][4];
-#pragma unroll
-            for (int a = 0; a < 8; ++a)
-#pragma unroll
-                for (int c = 0; c < 4; ++c) l1_i[a][c] = 0.f;
-#pragma unroll 4
-            for (int k = 0; k < KC; ++k) {
-                const float4 xa = *reinterpret_cast<const float4*>(cur.lx + k * LDI + ty * 8);
-                const float4 xb = *reinterpret_cast<const float4*>(cur.lx + k * LDI + ty * 8 + 4);
-                const float4 yv = *reinterpret_cast<const float4*>(cur.ly + k * LDJ + tx * 4);
-                const float xs[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
-                const float ys[4] = {yv.x, yv.y, yv.z, yv.w};
-#pragma unroll
-                for (int a = 0; a < 8; ++a)
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) l1_i[a][c] += fabsf(xs[a] - ys[c]);
-            }
-#pragma unroll
-            for (int a = 0; a < 8; ++a)
-#pragma unroll
-                for (int c = 0; c < 4; ++c) l1[a][c] += l1_i[a][c];
-            if (more) deposit(st[(g + 1) & 1]);
-            __syncthreads();
+    if (tid == 0) {
+        for (int i = 0; i < kL1Stages; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], 8);                            // one arrival per consumer warp
         }
-#pragma unroll
-        for (int a = 0; a < 8; ++a) {
-            const long long i = i0 + ty * 8 + a;
-            if (i >= row_end) continue;
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const long long j = j0 + tx * 4 + c;
-                if (j < col_end) l1_out[(static_cast<long long>(s) * n_rows_out + (i - row_begin)) * n_cols_out + (j - col_begin)] = l1[a][c];
+        fence_barrier_init();
+    }
+    __syncthreads();
+
+    if (warp == 8) {
+        if (lane == 0) {
+            // blocks past the operand's last one (a tile that hangs over the end) are clamped: their pairs are never stored
+            const long long n_rb = (rows.count + kQBlock - 1) / kQBlock, n_cb = (cols.count + kQBlock - 1) / kQBlock;
+            const uint32_t* x0 = rows.logq + (min(2 * rt, n_rb - 1) * seg.dp + seg.pad_off[s]) * kQBlock;
+            const uint32_t* x1 = rows.logq + (min(2 * rt + 1, n_rb - 1) * seg.dp + seg.pad_off[s]) * kQBlock;
+            const uint32_t* y = cols.logq + (min(cb, n_cb - 1) * seg.dp + seg.pad_off[s]) * kQBlock;
+            for (long long g = 0; g < stages; ++g) {
+                const int st = static_cast<int>(g % kL1Stages);
+                if (g >= kL1Stages) mbar_wait_backoff(&empty[st], static_cast<uint32_t>((g / kL1Stages - 1) & 1));
+                uint8_t* dst = smem_raw + st * L1Smem::kStage;
+                const long long off = g * (kL1KC * kQBlock);
+                mbar_arrive_expect_tx(&full[st], L1Smem::kStage);
+                bulk_copy_g2s(dst, x0 + off, kL1Piece, &full[st]);
+                bulk_copy_g2s(dst + kL1Piece, x1 + off, kL1Piece, &full[st]);
+                bulk_copy_g2s(dst + 2 * kL1Piece, y + off, kL1Piece, &full[st]);
             }
+        }
+        return;
+    }
+
+    const int tx = tid & 15, ty = tid >> 4;
+    const uint32_t x_word = (ty >> 3) * (kL1Piece / 4) + (ty & 7) * 8, y_word = 2 * (kL1Piece / 4) + tx * 4;
+    float l1[8][4];
+    uint32_t acc[8][4];
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            l1[a][c] = 0.f;
+            acc[a][c] = 0u;
+        }
+    for (long long g = 0; g < stages; ++g) {
+        const int st = static_cast<int>(g % kL1Stages);
+        mbar_wait(&full[st], static_cast<uint32_t>((g / kL1Stages) & 1));
+        const uint32_t* sx = reinterpret_cast<const uint32_t*>(smem_raw + st * L1Smem::kStage) + x_word;
+        const uint32_t* sy = reinterpret_cast<const uint32_t*>(smem_raw + st * L1Smem::kStage) + y_word;
+#pragma unroll 8
+        for (int k = 0; k < kL1KC; ++k) {
+            const uint4 xa = *reinterpret_cast<const uint4*>(sx + k * kQBlock);
+            const uint4 xb = *reinterpret_cast<const uint4*>(sx + k * kQBlock + 4);
+            const uint4 yv = *reinterpret_cast<const uint4*>(sy + k * kQBlock);
+            const uint32_t xs[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+            const uint32_t ys[4] = {yv.x, yv.y, yv.z, yv.w};
+#pragma unroll
+            for (int a = 0; a < 8; ++a)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[a][c] = __usad(xs[a], ys[c], acc[a][c]);
+        }
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&empty[st])) : "memory");
+        if ((g % (kChunk / kL1KC)) == kChunk / kL1KC - 1) {
+#pragma unroll
+            for (int a = 0; a < 8; ++a)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    l1[a][c] = fmaf(__uint2float_rn(acc[a][c]), 1.0f / kFixScale, l1[a][c]);
+                    acc[a][c] = 0u;
+                }
+        }
+    }
+    const long long n_rows_out = row_end - row_begin, n_cols_out = col_end - col_begin;
+#pragma unroll
+    for (int a = 0; a < 8; ++a) {
+        const long long i = rt * TI + ty * 8 + a;
+        if (i < row_begin || i >= row_end) continue;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const long long j = cb * TJ + tx * 4 + c;
+            if (j >= col_begin && j < col_end)
+                l1_out[(static_cast<long long>(s) * n_rows_out + (i - row_begin)) * n_cols_out + (j - col_begin)] = l1[a][c];
         }
     }
 }
@@ -409,8 +474,11 @@ int launch_distance(const DistOperand& rows, const DistOperand& cols, const Segm
     TOPO_CUDA(cudaEventRecord(ss->join, ss->stream));
     s = main_stream;
     {
-        const dim3 grid(static_cast<unsigned>((nc + TJ - 1) / TJ), static_cast<unsigned>((nr + TI - 1) / TI));
-        l1_kernel<<<grid, 256, 0, s>>>(rows, cols, seg, row_begin, row_end, col_begin, col_end, l1);
+        const int64_t rt0 = row_begin / TI, rt1 = (row_end + TI - 1) / TI;
+        const int64_t cb0 = col_begin / TJ, cb1 = (col_end + TJ - 1) / TJ;
+        if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(l1_kernel), L1Smem::kTotal)) return rc;
+        const dim3 grid(static_cast<unsigned>(cb1 - cb0), static_cast<unsigned>(rt1 - rt0), static_cast<unsigned>(seg.n));
+        l1_kernel<<<grid, kL1Threads, L1Smem::kTotal, s>>>(rows, cols, seg, rt0, cb0, row_begin, row_end, col_begin, col_end, l1);
     }
     TOPO_CUDA(cudaStreamWaitEvent(main_stream, ss->join, 0));
     {
@@ -438,14 +506,21 @@ extern "C" int64_t topo_distance_image_bytes(int64_t n, const int64_t* seg_len, 
     return (n + kRowsPerBlock - 1) / kRowsPerBlock * (seg.dp / kChunk) * static_cast<int64_t>(kChunkBytes);
 }
 
+extern "C" int64_t topo_distance_logq_words(int64_t n, const int64_t* seg_len, int n_scales) {
+    if (!seg_len || n_scales < 1 || n_scales > kMaxScales || n < 0) return -1;
+    return (n + kQBlock - 1) / kQBlock * kQBlock * make_segments(seg_len, n_scales).dp;
+}
+
 extern "C" int64_t topo_distance_workspace_floats(int64_t n_rows, int64_t n_cols, int n_scales) {
     if (n_rows < 0 || n_cols < 0 || n_scales < 1 || n_scales > kMaxScales) return -1;
     return 2 * static_cast<int64_t>(n_scales) * n_rows * n_cols;
 }
 
 extern "C" int topo_distance_prepare(const float* spec, int64_t n, int64_t d, const int64_t* seg_len, int n_scales,
-                                     float log_eps, float* logspec_p, void* image, float* sq_mean, topo_stream_t stream) {
-    TOPO_REQUIRE(spec && seg_len && logspec_p && image && sq_mean, "null argument");
+                                     float log_eps, uint32_t* logq, void* image, float* sq_mean, topo_stream_t stream) {
+    TOPO_REQUIRE(spec && seg_len && logq && image && sq_mean, "null argument");
+    TOPO_REQUIRE(log_eps >= 1e-17f, "log_eps below 1e-17 leaves the fixed-point window of the L1 term ([-40, 24) in log units)");
+    TOPO_REQUIRE((reinterpret_cast<uintptr_t>(logq) & 15) == 0, "logq must be 16-byte aligned");
     TOPO_REQUIRE(n_scales >= 1 && n_scales <= kMaxScales, "n_scales must be in [1, 8]");
     TOPO_REQUIRE(n >= 0 && n < (int64_t(1) << 31), "bad n");
     TOPO_REQUIRE((reinterpret_cast<uintptr_t>(image) & 1023) == 0, "the operand image must be 1024-byte aligned");
@@ -458,35 +533,37 @@ extern "C" int topo_distance_prepare(const float* spec, int64_t n, int64_t d, co
     TOPO_REQUIRE(total == d, "segment lengths do not add up to d");
     if (n == 0) return TOPO_OK;
     distance_prepare_kernel<<<dim3(static_cast<unsigned>(n), n_scales), 256, 0, as_stream(stream)>>>(
-        spec, d, seg, log_eps, logspec_p, static_cast<uint8_t*>(image), sq_mean);
+        spec, d, seg, static_cast<uint8_t*>(image), sq_mean);
+    distance_logq_kernel<<<dim3(static_cast<unsigned>(seg.dp / kChunk), static_cast<unsigned>((n + kQBlock - 1) / kQBlock)), 256, 0,
+                           as_stream(stream)>>>(spec, n, d, seg, log_eps, logq);
     TOPO_LAUNCH_CHECK();
     return TOPO_OK;
 }
 
-extern "C" int topo_distance_rows(const float* logspec_p, const void* image, const float* sq_mean, int64_t n,
+extern "C" int topo_distance_rows(const uint32_t* logq, const void* image, const float* sq_mean, int64_t n,
                                   const int64_t* seg_len, int n_scales, int64_t row_begin, int64_t row_end,
                                   int64_t col_begin, int64_t col_end, float* workspace, float* out, topo_stream_t stream) {
-    TOPO_REQUIRE(logspec_p && image && sq_mean && seg_len && workspace && out, "null argument");
+    TOPO_REQUIRE(logq && image && sq_mean && seg_len && workspace && out, "null argument");
     TOPO_REQUIRE(n_scales >= 1 && n_scales <= kMaxScales, "n_scales must be in [1, 8]");
     TOPO_REQUIRE(0 <= row_begin && row_begin <= row_end && row_end <= n, "bad row range");
     TOPO_REQUIRE(0 <= col_begin && col_begin <= col_end && col_end <= n, "bad column range");
     if (row_begin == row_end || col_begin == col_end) return TOPO_OK;
     const Segments seg = make_segments(seg_len, n_scales);
-    const DistOperand all{logspec_p, static_cast<const uint8_t*>(image), sq_mean, n, 0};
+    const DistOperand all{logq, static_cast<const uint8_t*>(image), sq_mean, n, 0};
     return launch_distance(all, all, seg, row_begin, row_end, col_begin, col_end, workspace, out, col_end - col_begin, stream);
 }
 
-extern "C" int topo_distance_block(const float* row_logspec, const void* row_image, const float* row_sq_mean, int64_t n_rows,
-                                   int64_t row_global0, const float* col_logspec, const void* col_image,
+extern "C" int topo_distance_block(const uint32_t* row_logq, const void* row_image, const float* row_sq_mean, int64_t n_rows,
+                                   int64_t row_global0, const uint32_t* col_logq, const void* col_image,
                                    const float* col_sq_mean, int64_t n_cols, int64_t col_global0, const int64_t* seg_len,
                                    int n_scales, float* workspace, float* out, int64_t ld_out, topo_stream_t stream) {
-    TOPO_REQUIRE(row_logspec && row_image && row_sq_mean && col_logspec && col_image && col_sq_mean && seg_len && workspace && out,
+    TOPO_REQUIRE(row_logq && row_image && row_sq_mean && col_logq && col_image && col_sq_mean && seg_len && workspace && out,
                  "null argument");
     TOPO_REQUIRE(n_scales >= 1 && n_scales <= kMaxScales, "n_scales must be in [1, 8]");
     TOPO_REQUIRE(n_rows >= 0 && n_cols >= 0 && row_global0 >= 0 && col_global0 >= 0 && ld_out >= n_cols, "bad block geometry");
     if (n_rows == 0 || n_cols == 0) return TOPO_OK;
     const Segments seg = make_segments(seg_len, n_scales);
-    const DistOperand rows{row_logspec, static_cast<const uint8_t*>(row_image), row_sq_mean, n_rows, row_global0};
-    const DistOperand cols{col_logspec, static_cast<const uint8_t*>(col_image), col_sq_mean, n_cols, col_global0};
+    const DistOperand rows{row_logq, static_cast<const uint8_t*>(row_image), row_sq_mean, n_rows, row_global0};
+    const DistOperand cols{col_logq, static_cast<const uint8_t*>(col_image), col_sq_mean, n_cols, col_global0};
     return launch_distance(rows, cols, seg, 0, n_rows, 0, n_cols, workspace, out, ld_out, stream);
 }

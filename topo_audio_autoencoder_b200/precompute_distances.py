@@ -55,8 +55,9 @@ def multiscale_spectrograms(audio: torch.Tensor, scales: Sequence[int] = SCALES)
 
 
 class PreparedSpectra:
-    """Operands of the pair reduction for one block of clips, resident on the device: the padded logs (FP32 pipe, L1 term),
-    the bf16x3 operand image of the spectra (tensor cores, Gram term; csrc/distance.cu) and per-scale mean squares."""
+    """Operands of the pair reduction for one block of clips, resident on the device: the logs as Q6.20 fixed point, k-major
+    inside 64-clip blocks (integer pipe, L1 term), the bf16x3 operand image of the spectra (tensor cores, Gram term;
+    csrc/distance.cu) and per-scale mean squares."""
 
     def __init__(self, spec: torch.Tensor, seg_len: Sequence[int], log_eps: float = LOG_EPSILON):
         spec = spec.contiguous()
@@ -67,8 +68,8 @@ class PreparedSpectra:
         self.dp = int(lib.topo_distance_padded_size(self.seg_c, n_scales))
         if self.dp < 0:
             raise ValueError("between 1 and 8 scales are supported")
-        dev = spec.device
-        self.logspec_p = torch.empty(self.n, self.dp, dtype=torch.float32, device=dev)
+        dev = self.device = spec.device
+        self.logq = torch.empty(int(lib.topo_distance_logq_words(self.n, self.seg_c, n_scales)), dtype=torch.int32, device=dev)
         image_bytes = int(lib.topo_distance_image_bytes(self.n, self.seg_c, n_scales))
         # rows past n in the last 128-clip block must read as zero; cudaMalloc'ed tensors are at least 512-byte aligned and
         # the caching allocator hands out 512-byte multiples: over-allocate to reach the 1024-byte alignment of the image
@@ -78,11 +79,11 @@ class PreparedSpectra:
         self.image = raw[shift:shift + image_bytes]
         self.sq_mean = torch.empty(self.n, n_scales, dtype=torch.float32, device=dev)
         check(lib.topo_distance_prepare(ptr(spec), self.n, self.d, self.seg_c, n_scales, float(log_eps),
-                                        ptr(self.logspec_p), self.image.data_ptr(), ptr(self.sq_mean), stream()))
+                                        self.logq.data_ptr(), self.image.data_ptr(), ptr(self.sq_mean), stream()))
 
     def _workspace(self, n_rows: int, n_cols: int) -> torch.Tensor:
         words = int(lib.topo_distance_workspace_floats(n_rows, n_cols, len(self.seg_len)))
-        return torch.empty(max(words, 1), dtype=torch.float32, device=self.logspec_p.device)
+        return torch.empty(max(words, 1), dtype=torch.float32, device=self.device)
 
     def block(self, cols: "PreparedSpectra", row_global0: int = 0, col_global0: int = 0,
               out: Optional[torch.Tensor] = None, workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -92,23 +93,23 @@ class PreparedSpectra:
         if cols.seg_len != self.seg_len:
             raise ValueError("row and column blocks were prepared with different scale segments")
         if out is None:
-            out = torch.empty(self.n, cols.n, dtype=torch.float32, device=self.logspec_p.device)
+            out = torch.empty(self.n, cols.n, dtype=torch.float32, device=self.device)
         # `out` may be a column window of a wider buffer (the running top-k merge): unit column stride, any row stride
         if not (out.is_cuda and out.dtype == torch.float32 and out.dim() == 2 and out.stride(1) == 1
                 and out.shape[0] >= self.n and out.shape[1] >= cols.n):
             raise ValueError("out must be a CUDA float32 [rows, >= columns] view with unit column stride")
         if workspace is None:
             workspace = self._workspace(self.n, cols.n)
-        check(lib.topo_distance_block(ptr(self.logspec_p), self.image.data_ptr(), ptr(self.sq_mean), self.n, int(row_global0),
-                                      ptr(cols.logspec_p), cols.image.data_ptr(), ptr(cols.sq_mean), cols.n, int(col_global0),
+        check(lib.topo_distance_block(self.logq.data_ptr(), self.image.data_ptr(), ptr(self.sq_mean), self.n, int(row_global0),
+                                      cols.logq.data_ptr(), cols.image.data_ptr(), ptr(cols.sq_mean), cols.n, int(col_global0),
                                       self.seg_c, len(self.seg_len), ptr(workspace), out.data_ptr(), out.stride(0), stream()))
         return out
 
     def rows(self, row_begin: int, row_end: int, col_begin: int = 0, col_end: Optional[int] = None) -> torch.Tensor:
         col_end = self.n if col_end is None else col_end
-        out = torch.empty(row_end - row_begin, col_end - col_begin, dtype=torch.float32, device=self.logspec_p.device)
+        out = torch.empty(row_end - row_begin, col_end - col_begin, dtype=torch.float32, device=self.device)
         workspace = self._workspace(row_end - row_begin, col_end - col_begin)
-        check(lib.topo_distance_rows(ptr(self.logspec_p), self.image.data_ptr(), ptr(self.sq_mean), self.n, self.seg_c,
+        check(lib.topo_distance_rows(self.logq.data_ptr(), self.image.data_ptr(), ptr(self.sq_mean), self.n, self.seg_c,
                                      len(self.seg_len), row_begin, row_end, col_begin, col_end, ptr(workspace), ptr(out), stream()))
         return out
 
