@@ -410,6 +410,24 @@ int topo_distance_block(const uint32_t* row_logq, const void* row_image, const f
                         int64_t n_cols, int64_t col_global0, const int64_t* seg_len, int n_scales, float* workspace,
                         float* out, int64_t ld_out, topo_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * (f)1. The decoder's cross-attention over the stage's compact rows (decoder.py:58-63, 144-162: nn.MultiheadAttention,
+ * head dimension 16, queries = the q_len rows made from a sample's vertices, memory = its active edges, triangles and
+ * tetrahedra).  q [batch, q_len, C], C = 16 * heads, already projected; k, v [rows, C] = the projected memory rows of ALL
+ * samples in the concatenated compact layout (rank 1 rows of every sample, then rank 2, then rank 3); seg [batch][3][2] int32 =
+ * (first row, row count) of sample b's run inside each rank: the memory is neither padded nor copied and no mask exists.
+ *   fwd: out [batch, q_len, C] = softmax(q k^T / 4) v per (sample, head); lse2 [batch, heads, q_len] = log2 of the softmax
+ *        denominator in the scaled log2 domain (kept for the backward)
+ *   bwd: dq, dk, dv (dk / dv rows outside every run are not written); d_row [batch, heads, q_len] scratch; max_run_len = the
+ *        longest run of any sample (sizes the key-parallel grid).  Two deterministic passes, no atomics.
+ * All buffers 16-byte aligned, fp32.
+ * ------------------------------------------------------------------------------------------- */
+int topo_cross_attention_fwd(const float* q, const float* k, const float* v, const int32_t* seg, int64_t batch,
+                             int64_t q_len, int heads, float* out, float* lse2, topo_stream_t stream);
+int topo_cross_attention_bwd(const float* q, const float* k, const float* v, const int32_t* seg, const float* out,
+                             const float* lse2, const float* d_out, int64_t batch, int64_t q_len, int heads,
+                             int64_t max_run_len, float* d_row, float* dq, float* dk, float* dv, topo_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -110,6 +110,8 @@ SIGNATURES = {
     "topo_distance_prepare": [_P, _I64, _I64, C.POINTER(_I64), _I32, _F, _P, _P, _P, _P],
     "topo_distance_rows": [_P, _P, _P, _I64, C.POINTER(_I64), _I32, _I64, _I64, _I64, _I64, _P, _P, _P],
     "topo_distance_block": [_P, _P, _P, _I64, _I64, _P, _P, _P, _I64, _I64, C.POINTER(_I64), _I32, _P, _P, _I64, _P],
+    "topo_cross_attention_fwd": [_P, _P, _P, _P, _I64, _I64, _I32, _P, _P, _P],
+    "topo_cross_attention_bwd": [_P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I32, _I64, _P, _P, _P, _P, _P],
 }
 _NON_STATUS = {"topo_version": C.c_int, "topo_last_error": C.c_char_p, "topo_tables_destroy": None,
                "topo_debug_fwd16_mask": None, "topo_debug_fwd16_stamps": None, "topo_debug_bwd_stamps": None,
@@ -161,7 +163,7 @@ KERNELS_PER_CALL = {
     "topo_operators_fill": 1, "topo_operators_bwd": 1, "topo_sccn_aggregate_fwd": 2, "topo_sccn_aggregate_bwd": 3,
     "topo_spmm_csr": 1, "topo_sddmm_csr": 1, "topo_sccn_prepare_images": 1, "topo_sccn_finish_weight_grads": 1, "topo_sccn_combine_fwd": 1, "topo_sccn_combine_fwd_tc": 1, "topo_sccn_combine_fwd_tc2": 1, "topo_sccn_combine_bwd": 2,
     "topo_sccn_combine_bwd_attention": 1, "topo_sccn_combine_bwd_conv": 1, "topo_sccn_combine_bwd_conv_tc": 1, "topo_sccn_combine_bwd_tc": 1, "topo_distance_prepare": 2,
-    "topo_distance_rows": 3, "topo_distance_block": 3,
+    "topo_distance_rows": 3, "topo_distance_block": 3, "topo_cross_attention_fwd": 1, "topo_cross_attention_bwd": 2,
 }
 
 

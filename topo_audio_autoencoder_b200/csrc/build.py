@@ -17,7 +17,7 @@ OUT = os.path.join(os.path.dirname(HERE), "libtopo_b200.so")
 # the product sources plus the unit-test GEMMs, compiled with -DTOPO_DEBUG_KERNELS=1: ablation knobs, globaltimer stamps and
 # the topo_debug_* entry points (tests/test_gpu_tc.py, scripts/ablate_*.py).  Never loaded by the package itself.
 OUT_DEBUG = os.path.join(os.path.dirname(HERE), "libtopo_b200_debug.so")
-SOURCES = ["tables.cu", "gate.cu", "rectifier.cu", "operators.cu", "aggregate.cu", "combine.cu", "combine_tc.cu", "weight_images.cu", "combine_fwd16.cu", "combine_bwd_tc.cu", "distance.cu"]
+SOURCES = ["tables.cu", "gate.cu", "rectifier.cu", "operators.cu", "aggregate.cu", "combine.cu", "combine_tc.cu", "weight_images.cu", "combine_fwd16.cu", "combine_bwd_tc.cu", "distance.cu", "attention.cu"]
 DEBUG_ONLY_SOURCES = ["gemm16_debug.cu"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
          "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",

@@ -11,8 +11,12 @@ and reproduces decoder.py:131-167 per sample without a Python loop over samples:
   * row-wise layers (x0.1, vertex_to_query, pre-attention LayerNorm, key / value projections) run once over all rows;
   * the temporal conv + interpolation along the vertex axis depend on a sample's active-vertex count, so samples are
     grouped by that count (at most n_vertices + 1 groups; one group when every vertex is active);
-  * the rank 1-3 rows of a sample become its attention memory, padded to the longest sample with a key-padding mask.
-An inactive row must never reach the memory: the compaction contract is checked by tests/test_gpu_decoder.py.
+  * the rank 1-3 rows of a sample are its attention memory WHERE THEY LIE: the scaled dot-product core of the
+    cross-attention runs in csrc/attention.cu over per-sample (first row, row count) runs of the compact layout -- no
+    padding to the longest sample, no key-padding mask, no scatter (on CPU tensors, for host-side tests, the stock module
+    runs on a padded copy instead).
+An inactive row must never reach the memory: the compaction contract is checked by tests/test_decoder_tail.py (CPU) and
+tests/test_gpu_decoder.py (the CUDA path).
 """
 from __future__ import annotations
 
@@ -34,6 +38,22 @@ class ScaleLayer(nn.Module):
 
     def forward(self, x):
         return x * self.scale_factor
+
+
+def interpolate_linear(x: torch.Tensor, size=None, scale_factor=None) -> torch.Tensor:
+    """``F.interpolate(x, mode="linear", align_corners=False)`` of a [B, C, T] signal, evaluated by the bilinear 2-D operator on
+    a height-1 image: the same weights and the same arithmetic (bit-identical on the CPU, forward and backward), but its CUDA
+    kernel spreads ALL output elements over the grid where the 1-D kernel gives one thread a whole output column (0.5 ms for
+    an 8 MB tensor on a B200: 22 ms per training step over the decoder's five interpolations and their backwards)."""
+    kw = dict(size=(1, size)) if size is not None else dict(scale_factor=(1.0, float(scale_factor)))
+    return F.interpolate(x.unsqueeze(2), mode="bilinear", align_corners=False, **kw).squeeze(2)
+
+
+class LinearUpsample(nn.Upsample):
+    """``nn.Upsample(scale_factor=k, mode="linear", align_corners=False)`` (decoder.py:93) through ``interpolate_linear``."""
+
+    def forward(self, x):
+        return interpolate_linear(x, scale_factor=self.scale_factor)
 
 
 class DecoderTail(nn.Module):
@@ -60,7 +80,7 @@ class DecoderTail(nn.Module):
         for i in range(4):
             cin, cout = channels[i], channels[min(i + 1, len(channels) - 1)]
             self.upsample_blocks.append(nn.Sequential(
-                nn.Upsample(scale_factor=2, mode="linear", align_corners=False),
+                LinearUpsample(scale_factor=2, mode="linear", align_corners=False),
                 nn.Conv1d(cin, cin, kernel_size=3, padding=1, groups=cin), nn.Conv1d(cin, cout, kernel_size=1),
                 nn.GroupNorm(min(8, cout), cout), nn.GELU(), ScaleLayer(1.0 / (2 ** (i + 1)))))
         self.apply(self._init_weights)                                                                         # :108
@@ -76,7 +96,7 @@ class DecoderTail(nn.Module):
     def attend(self, output: Dict[str, Optional[torch.Tensor]]) -> torch.Tensor:
         v = self.vertex_to_query(output["rank_0"] * 0.1)                                                       # :132-133
         q = self.temporal_conv(v.transpose(0, 1).unsqueeze(0))                                                 # :136-137
-        q = F.interpolate(q, size=self.initial_sequence_length, mode="linear", align_corners=False).transpose(1, 2)   # :140-141
+        q = interpolate_linear(q, size=self.initial_sequence_length).transpose(1, 2)                          # :140-141
         mem = [output[f"rank_{r}"] * 0.1 for r in range(1, 4) if output.get(f"rank_{r}") is not None]          # :144-150
         mem = self.pre_attention_norm(torch.cat(mem, dim=0).unsqueeze(0))                                      # :153-156
         q = self.pre_attention_norm(q)
@@ -114,16 +134,40 @@ class DecoderTail(nn.Module):
             members = torch.nonzero(counts[:, 0] == n0).squeeze(1)
             idx = (starts0[members].unsqueeze(1) + torch.arange(n0).unsqueeze(0)).to(dev)                    # [g, n0]
             grp = v[idx].transpose(1, 2)                                                                       # [g, C, n0]
-            grp = F.interpolate(self.temporal_conv(grp), size=self.initial_sequence_length, mode="linear", align_corners=False)
+            grp = interpolate_linear(self.temporal_conv(grp), size=self.initial_sequence_length)
             q[members.to(dev)] = grp.transpose(1, 2)
         q = self.pre_attention_norm(q)
-        # memory: the rank 1..3 rows of every sample, in rank order, padded to the longest sample
+        # memory: the rank 1..3 rows of every sample, rank after rank, exactly as the stage emits them
         rows = torch.cat([xs[r][:tot[r]] for r in (1, 2, 3)], dim=0) * 0.1
         rows = self.pre_attention_norm(rows)
         keys, values = self.key_proj(rows), self.value_proj(rows)
-        m_max = int(mem_len.max())
         base = [0, tot[1], tot[1] + tot[2]]
         starts = [torch.cumsum(counts[:, r], 0) - counts[:, r] for r in (1, 2, 3)]
+        if keys.is_cuda:
+            a = self._attend_compact(q, keys, values, counts, base, starts)
+        else:
+            a = self._attend_padded(q, keys, values, counts, base, starts, mem_len)
+        return self.post_attention_norm(q + F.gelu(a * self.attention_scale))
+
+    def _attend_compact(self, q, keys, values, counts, base, starts):
+        """CUDA: nn.MultiheadAttention's arithmetic (F.multi_head_attention_forward: packed in-projection, scaled dot-product
+        per head, out-projection) with the scaled dot-product core on the compact rows (csrc/attention.cu) -- the memory is
+        neither padded nor scattered, each sample attends over its own three runs of rows."""
+        from .attention import segment_cross_attention
+        mha, h = self.cross_attention, self.hidden
+        w, bias = mha.in_proj_weight, mha.in_proj_bias
+        seg = torch.stack([torch.stack([base[j] + starts[j], counts[:, r]], dim=1) for j, r in enumerate((1, 2, 3))], dim=1)
+        seg = seg.to(torch.int32).contiguous().to(q.device, non_blocking=True)
+        qp = F.linear(q, w[:h], bias[:h])
+        kp = F.linear(keys, w[h:2 * h], bias[h:2 * h])
+        vp = F.linear(values, w[2 * h:], bias[2 * h:])
+        a = segment_cross_attention(qp, kp, vp, seg, mha.num_heads, int(counts[:, 1:].max()))
+        return F.linear(a, mha.out_proj.weight, mha.out_proj.bias)
+
+    def _attend_padded(self, q, keys, values, counts, base, starts, mem_len):
+        """CPU tensors (host-side tests): the stock module on a memory padded to the longest sample, with a key-padding mask."""
+        b, dev, h = counts.shape[0], q.device, self.hidden
+        m_max = int(mem_len.max())
         sample_of, slot_of, src = [], [], []
         offset_in_sample = torch.zeros(b, dtype=torch.int64)
         for j, r in enumerate((1, 2, 3)):
@@ -141,7 +185,7 @@ class DecoderTail(nn.Module):
         v_pad[sample_of, slot_of] = values[src]
         pad_mask = (torch.arange(m_max).unsqueeze(0) >= mem_len.unsqueeze(1)).to(dev)
         a, _ = self.cross_attention(query=q, key=k_pad, value=v_pad, key_padding_mask=pad_mask, need_weights=False)
-        return self.post_attention_norm(q + F.gelu(a * self.attention_scale))
+        return a
 
     def forward_batched(self, xs: Sequence[torch.Tensor], counts: torch.Tensor) -> torch.Tensor:
         """-> [B, output_channels, 16 L] band signals (decoder.py:170-175)."""

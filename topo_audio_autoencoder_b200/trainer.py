@@ -27,9 +27,15 @@ class Trainer:
     def __init__(self, model, checkpoint_dir: Optional[str] = None, encoder_lr: float = 1e-3, decoder_lr: float = 1e-4,
                  initial_reg_factor: float = 0.00001, invalid_state_penalty: float = 100.0, device: str = "cuda",
                  seed: int = 511990, initial_temp: float = 5.0, min_temp: float = 0.1, temp_decay: float = 0.95,
-                 gradient_clip_val: float = 10.0, accumulate_grad_batches: int = 4, bucket_cap_mb: int = 25):
+                 gradient_clip_val: float = 10.0, accumulate_grad_batches: int = 4, bucket_cap_mb: int = 25,
+                 cudnn_benchmark: bool = True):
         torch.manual_seed(seed)                                                                   # :462-469
         self.device = torch.device(device)
+        if cudnn_benchmark and self.device.type == "cuda":
+            # The stock front-end and decoder convolutions see the same shapes every step: let cuDNN time its algorithms once
+            # (process-wide PyTorch switch; fp32 results stay within the spread of cuDNN's own algorithms).  Measured on a
+            # B200: 22 ms of a 178 ms step, mostly the grouped convolutions' data gradient.
+            torch.backends.cudnn.benchmark = True
         self.model = model.to(self.device)
         self.checkpoint_dir = Path(checkpoint_dir) if checkpoint_dir is not None else None
         if self.checkpoint_dir is not None:
