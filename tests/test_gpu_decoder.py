@@ -175,3 +175,28 @@ def test_kernel_equals_stock_multihead_attention_on_padded_memory():
     a = tail._attend_compact(q, keys, values, counts, base, starts)
     b = tail._attend_padded(q, keys, values, counts, base, starts, counts[:, 1:].sum(1))
     assert_close("decoder/compact-vs-padded-mha", a, b, rtol=1e-5, atol=2e-6)
+
+
+@pytest.mark.parametrize("c", [32, 64, 128])
+def test_row_layernorm_kernel_against_torch(c):
+    """topo_layernorm_fwd/bwd at the consumer's sizes (row counts that do not divide the rows-per-warp grouping), 2-D and 3-D inputs"""
+    from topo_audio_autoencoder_b200.decoder import RowLayerNorm
+    g = torch.Generator().manual_seed(c)
+    ln = RowLayerNorm(c).cuda()
+    with torch.no_grad():
+        ln.weight.copy_(1 + 0.1 * torch.randn(c, generator=g))
+        ln.bias.copy_(0.1 * torch.randn(c, generator=g))
+    for shape in [(100003, c), (7, 251, c), (1, c)]:
+        x = (torch.randn(shape, generator=g) * 3 + 0.5).cuda().requires_grad_(True)
+        up = torch.randn(shape, generator=g).cuda()
+        y = ln(x)
+        gx, gw, gb = torch.autograd.grad(y, (x, ln.weight, ln.bias), up)
+        x64 = x.detach().double().requires_grad_(True)
+        w64, b64 = ln.weight.detach().double().requires_grad_(True), ln.bias.detach().double().requires_grad_(True)
+        ref = F.layer_norm(x64, (c,), w64, b64, ln.eps)
+        rx, rw, rb = torch.autograd.grad(ref, (x64, w64, b64), up.double())
+        tag = f"row-layernorm/C={c}/{'x'.join(map(str, shape))}"
+        assert_close(tag + "/y", y, ref.float(), rtol=1e-5, atol=1e-6)
+        assert_close(tag + "/dx", gx, rx.float(), rtol=1e-5, atol=2e-6)
+        assert_close(tag + "/dgamma", gw, rw.float(), rtol=1e-5, atol=1e-5 * rw.abs().max().item())
+        assert_close(tag + "/dbeta", gb, rb.float(), rtol=1e-5, atol=1e-5 * rb.abs().max().item())

@@ -766,81 +766,121 @@ __global__ void __launch_bounds__(NT) combine_bwd_conv_kernel(topo_combine_param
 }
 
 // ---------------------------------------------------------------------------------------------
-// Row LayerNorm (one warp per row) and the active-embedding scaling
+// Row LayerNorm and the active-embedding scaling
+//
+// LayerNorm over [rows, C], C = 32 / 64 / 128: C / 4 lanes hold one row as float4s, a warp holds 32 / (C / 4) rows and
+// works on two such groups per iteration (all of their loads are issued before the first shuffle), so a few thousand
+// warps keep enough bytes in flight for HBM: the decoder consumer normalises 395,200 memory rows five times per
+// micro-batch (decoder.py:70-83, 153-156), where a one-row-per-warp kernel reaches a tenth of the bandwidth.
 // ---------------------------------------------------------------------------------------------
-template <int VEC>
+// 128-bit read-only load, issued where it is written (the two row groups of an iteration are fetched before the first shuffle)
+__device__ __forceinline__ float4 ldg_stream(const float4* p) {
+    float4 v;
+    asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
+
+template <int LPR>
+__device__ __forceinline__ float group_sum(float v) {      // over the LPR adjacent lanes that share a row
+#pragma unroll
+    for (int o = 1; o < LPR; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <int C>
 __global__ void __launch_bounds__(256) layernorm_fwd_kernel(long long rows, const float* __restrict__ x,
                                                             const float* __restrict__ gamma,
                                                             const float* __restrict__ beta, float eps,
                                                             float* __restrict__ y) {
-    constexpr int C = VEC * 32;
-    const int lane = threadIdx.x & 31;
-    Vec<VEC> g, b;
-    g.load(gamma + lane * VEC);
-    b.load(beta + lane * VEC);
-    for (long long row = blockIdx.x * 8ll + (threadIdx.x >> 5); row < rows; row += gridDim.x * 8ll) {
-        Vec<VEC> v;
-        v.load(x + row * C + lane * VEC);
-        float s = 0.f;
+    constexpr int LPR = C / 4, RPW = 32 / LPR;
+    const int lane = threadIdx.x & 31, sub = lane % LPR, rw = lane / LPR;
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + sub);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + sub);
+    const long long step = static_cast<long long>(gridDim.x) * 8 * RPW;
+    for (long long row0 = (blockIdx.x * 8ll + (threadIdx.x >> 5)) * RPW; row0 < rows; row0 += 2 * step) {
+        long long row[2] = {row0 + rw, row0 + step + rw};
+        float4 v[2];
 #pragma unroll
-        for (int k = 0; k < VEC; ++k) s += v.v[k];
-        const float mean = warp_sum(s) * (1.0f / C);
-        float q = 0.f;
+        for (int u = 0; u < 2; ++u)
+            v[u] = row[u] < rows ? ldg_stream(reinterpret_cast<const float4*>(x + row[u] * C) + sub) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int k = 0; k < VEC; ++k) q = fmaf(v.v[k] - mean, v.v[k] - mean, q);
-        const float rstd = 1.0f / sqrtf(warp_sum(q) * (1.0f / C) + eps);
-#pragma unroll
-        for (int k = 0; k < VEC; ++k) v.v[k] = fmaf((v.v[k] - mean) * rstd, g.v[k], b.v[k]);
-        v.store(y + row * C + lane * VEC);
+        for (int u = 0; u < 2; ++u) {
+            const float mean = group_sum<LPR>((v[u].x + v[u].y) + (v[u].z + v[u].w)) * (1.0f / C);
+            const float d0 = v[u].x - mean, d1 = v[u].y - mean, d2 = v[u].z - mean, d3 = v[u].w - mean;
+            const float rstd = 1.0f / sqrtf(group_sum<LPR>(fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, d3 * d3)))) * (1.0f / C) + eps);
+            if (row[u] < rows)
+                *(reinterpret_cast<float4*>(y + row[u] * C) + sub) =
+                    make_float4(fmaf(d0 * rstd, g.x, b.x), fmaf(d1 * rstd, g.y, b.y), fmaf(d2 * rstd, g.z, b.z), fmaf(d3 * rstd, g.w, b.w));
+        }
     }
 }
 
-template <int VEC>
+template <int C>
 __global__ void __launch_bounds__(256) layernorm_bwd_kernel(long long rows, const float* __restrict__ x,
                                                             const float* __restrict__ gamma, float eps,
                                                             const float* __restrict__ gy_in,
                                                             float* __restrict__ gx, float* __restrict__ g_gamma,
                                                             float* __restrict__ g_beta) {
-    constexpr int C = VEC * 32;
-    const int lane = threadIdx.x & 31;
-    Vec<VEC> g;
-    g.load(gamma + lane * VEC);
-    float pg[VEC], pb[VEC];
+    constexpr int LPR = C / 4, RPW = 32 / LPR;
+    __shared__ float red[8][2][C];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sub = lane % LPR, rw = lane / LPR;
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + sub);
+    float pg[4] = {0.f, 0.f, 0.f, 0.f}, pb[4] = {0.f, 0.f, 0.f, 0.f};
+    const long long step = static_cast<long long>(gridDim.x) * 8 * RPW;
+    for (long long row0 = (blockIdx.x * 8ll + warp) * RPW; row0 < rows; row0 += 2 * step) {
+        long long row[2] = {row0 + rw, row0 + step + rw};
+        float4 v[2], dy[2];
 #pragma unroll
-    for (int k = 0; k < VEC; ++k) pg[k] = pb[k] = 0.f;
-    for (long long row = blockIdx.x * 8ll + (threadIdx.x >> 5); row < rows; row += gridDim.x * 8ll) {
-        Vec<VEC> v, dy;
-        v.load(x + row * C + lane * VEC);
-        dy.load(gy_in + row * C + lane * VEC);
-        float s = 0.f;
-#pragma unroll
-        for (int k = 0; k < VEC; ++k) s += v.v[k];
-        const float mean = warp_sum(s) * (1.0f / C);
-        float q = 0.f;
-#pragma unroll
-        for (int k = 0; k < VEC; ++k) q = fmaf(v.v[k] - mean, v.v[k] - mean, q);
-        const float rstd = 1.0f / sqrtf(warp_sum(q) * (1.0f / C) + eps);
-        float c1 = 0.f, c2 = 0.f, xh[VEC], gyv[VEC];
-#pragma unroll
-        for (int k = 0; k < VEC; ++k) {
-            xh[k] = (v.v[k] - mean) * rstd;
-            pg[k] = fmaf(dy.v[k], xh[k], pg[k]);
-            pb[k] += dy.v[k];
-            gyv[k] = dy.v[k] * g.v[k];
-            c1 += gyv[k];
-            c2 = fmaf(gyv[k], xh[k], c2);
+        for (int u = 0; u < 2; ++u) {
+            const bool ok = row[u] < rows;
+            v[u] = ok ? ldg_stream(reinterpret_cast<const float4*>(x + row[u] * C) + sub) : make_float4(0.f, 0.f, 0.f, 0.f);
+            dy[u] = ok ? ldg_stream(reinterpret_cast<const float4*>(gy_in + row[u] * C) + sub) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        c1 = warp_sum(c1) * (1.0f / C);
-        c2 = warp_sum(c2) * (1.0f / C);
-        Vec<VEC> o;
 #pragma unroll
-        for (int k = 0; k < VEC; ++k) o.v[k] = rstd * (gyv[k] - c1 - xh[k] * c2);
-        o.store(gx + row * C + lane * VEC);
+        for (int u = 0; u < 2; ++u) {
+            const float mean = group_sum<LPR>((v[u].x + v[u].y) + (v[u].z + v[u].w)) * (1.0f / C);
+            const float d[4] = {v[u].x - mean, v[u].y - mean, v[u].z - mean, v[u].w - mean};
+            const float rstd = 1.0f / sqrtf(group_sum<LPR>(fmaf(d[0], d[0], fmaf(d[1], d[1], fmaf(d[2], d[2], d[3] * d[3])))) * (1.0f / C) + eps);
+            const float dyv[4] = {dy[u].x, dy[u].y, dy[u].z, dy[u].w};
+            const float gv[4] = {g.x, g.y, g.z, g.w};
+            float xh[4], gyv[4], c1 = 0.f, c2 = 0.f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                xh[k] = d[k] * rstd;
+                pg[k] = fmaf(dyv[k], xh[k], pg[k]);        // rows past the end contribute dy = 0
+                pb[k] += dyv[k];
+                gyv[k] = dyv[k] * gv[k];
+                c1 += gyv[k];
+                c2 = fmaf(gyv[k], xh[k], c2);
+            }
+            c1 = group_sum<LPR>(c1) * (1.0f / C);
+            c2 = group_sum<LPR>(c2) * (1.0f / C);
+            if (row[u] < rows)
+                *(reinterpret_cast<float4*>(gx + row[u] * C) + sub) =
+                    make_float4(rstd * (gyv[0] - c1 - xh[0] * c2), rstd * (gyv[1] - c1 - xh[1] * c2),
+                                rstd * (gyv[2] - c1 - xh[2] * c2), rstd * (gyv[3] - c1 - xh[3] * c2));
+        }
     }
+    // column sums: over the warp's row groups in shuffles, over the CTA's warps in shared memory, one atomic per column and CTA
 #pragma unroll
-    for (int k = 0; k < VEC; ++k) {
-        atomicAdd(g_gamma + lane * VEC + k, pg[k]);
-        atomicAdd(g_beta + lane * VEC + k, pb[k]);
+    for (int k = 0; k < 4; ++k) {
+#pragma unroll
+        for (int o = LPR; o < 32; o <<= 1) {
+            pg[k] += __shfl_xor_sync(0xffffffffu, pg[k], o);
+            pb[k] += __shfl_xor_sync(0xffffffffu, pb[k], o);
+        }
+        if (rw == 0) {
+            red[warp][0][4 * sub + k] = pg[k];
+            red[warp][1][4 * sub + k] = pb[k];
+        }
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < 2 * C; idx += 256) {
+        const int which = idx / C, col = idx % C;
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += red[w][which][col];
+        atomicAdd((which == 0 ? g_gamma : g_beta) + col, t);
     }
 }
 
@@ -1054,8 +1094,10 @@ extern "C" int topo_layernorm_fwd(int64_t rows, int channels, const float* x, co
                                   const float* beta, float eps, float* y, topo_stream_t stream) {
     TOPO_REQUIRE(rows >= 0 && x && gamma && beta && y, "bad argument");
     if (rows == 0) return TOPO_OK;
+    TOPO_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(gamma) |
+                   reinterpret_cast<uintptr_t>(beta)) & 15) == 0, "buffers must be 16-byte aligned");
     const int grid = static_cast<int>(std::min<int64_t>((rows + 7) / 8, sm_count() * 8));
-    DISPATCH_VEC(channels, (layernorm_fwd_kernel<VEC><<<grid, 256, 0, as_stream(stream)>>>(rows, x, gamma, beta, eps, y)));
+    DISPATCH_VEC(channels, (layernorm_fwd_kernel<VEC * 32><<<grid, 256, 0, as_stream(stream)>>>(rows, x, gamma, beta, eps, y)));
     TOPO_LAUNCH_CHECK();
     return TOPO_OK;
 }
@@ -1065,8 +1107,10 @@ extern "C" int topo_layernorm_bwd(int64_t rows, int channels, const float* x, co
                                   topo_stream_t stream) {
     TOPO_REQUIRE(rows >= 0 && x && gamma && grad_y && grad_x && grad_gamma && grad_beta, "bad argument");
     if (rows == 0) return TOPO_OK;
-    const int grid = static_cast<int>(std::min<int64_t>((rows + 7) / 8, sm_count() * 2));
-    DISPATCH_VEC(channels, (layernorm_bwd_kernel<VEC><<<grid, 256, 0, as_stream(stream)>>>(
+    TOPO_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(grad_y) | reinterpret_cast<uintptr_t>(grad_x) |
+                   reinterpret_cast<uintptr_t>(gamma)) & 15) == 0, "buffers must be 16-byte aligned");
+    const int grid = static_cast<int>(std::min<int64_t>((rows + 7) / 8, sm_count() * 4));
+    DISPATCH_VEC(channels, (layernorm_bwd_kernel<VEC * 32><<<grid, 256, 0, as_stream(stream)>>>(
                                rows, x, gamma, eps, grad_y, grad_x, grad_gamma, grad_beta)));
     TOPO_LAUNCH_CHECK();
     return TOPO_OK;
