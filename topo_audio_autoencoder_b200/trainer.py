@@ -41,7 +41,8 @@ class Trainer:
         if self.checkpoint_dir is not None:
             self.checkpoint_dir.mkdir(parents=True, exist_ok=True)
         self.optimizer = Adam([{"params": self.model.encoder.parameters(), "lr": encoder_lr},     # :81-87
-                               {"params": self.model.decoder.parameters(), "lr": decoder_lr}])
+                               {"params": self.model.decoder.parameters(), "lr": decoder_lr}],
+                              fused=self.device.type == "cuda")          # one multi-tensor kernel per group on the GPU, same update
         self.loss_fn = AutoencoderLoss(binary_entropy_penalty=initial_reg_factor, min_entropy_penalty=0.01,
                                        complexity_penalty=0.1)                                   # :97-101
         self.invalid_state_penalty = invalid_state_penalty
