@@ -269,7 +269,14 @@ typedef struct {
     float* g_att_b2;
     float* g_ln_gamma;
     float* g_ln_beta;
+    /* topo_sccn_combine_bwd_tc only.  NULL: the parameter gradients above are ACCUMULATED with floating-point atomics (their
+     * low bits depend on the order the CTAs finish in).  Otherwise: [CTAs of the launch][TOPO_CTA_PARTIAL_FLOATS] scratch --
+     * CTA b stores its own partial sums at slot b ([w1 C*C][wprod_0..2 C*C each][b1 C][w2 C][gamma C][beta C][b2 1]) with plain
+     * stores, the seven pointers above are NOT touched, and topo_sccn_finish_weight_grads adds the slots in CTA order:
+     * bit-reproducible parameter gradients.  The launch uses topo_sccn_combine_grid(rows, max_ctas) CTAs. */
+    float* cta_partials;
 } topo_combine_grads;
+#define TOPO_CTA_PARTIAL_FLOATS 16704
 
 /* bf16x3 operand images of the weights (csrc/weight_images.cu), built once per layer and step and shared by the
  * forward and backward tensor-core kernels of all ranks.  A job with `w` writes the image of W_k [in][out]
@@ -284,16 +291,29 @@ typedef struct {
 #define TOPO_WEIGHT_IMAGE_BYTES 24576
 int topo_sccn_prepare_images(const topo_image_job* jobs, int n_jobs, int channels, topo_stream_t stream);
 
-/* The tail of the conv-weight chain for up to 96 messages in one launch (one CTA each, deterministic):
- *   g_w = scale * wprod   ([C, C]),   g_scale[0] = <w, wprod>      with wprod = g_wprod of topo_combine_grads. */
+/* The tail of the parameter-gradient chain for up to 96 jobs in one launch (one CTA each, deterministic).  With p = wprod
+ * (accumulated by the backward) or, when `partials` is set, p[i] = sum over the launch's active CTAs b, in order, of
+ * partials[b * TOPO_CTA_PARTIAL_FLOATS + partial_offset + i]  (active = min(topo_sccn_combine_grid(rows, max_ctas),
+ * ceil(min(*n_rows_dev, rows) / 128)); n_rows_dev may be NULL):
+ *   w != NULL:  g_w = scale * p  ([count] elements),  g_scale[0] = <w, p>      (conv weights: count = C * C)
+ *   w == NULL:  g_w = p                                                          (attention / LayerNorm parameters) */
 typedef struct {
     const float* wprod;
     const float* w;
     const float* scale;
     float* g_w;
     float* g_scale;
+    const float* partials;
+    const int32_t* n_rows_dev;
+    int64_t rows;
+    int32_t partial_offset;
+    int32_t count;           /* 0 = channels * channels */
+    int32_t max_ctas;
+    int32_t reserved_;
 } topo_wgrad_job;
 int topo_sccn_finish_weight_grads(const topo_wgrad_job* jobs, int n_jobs, int channels, topo_stream_t stream);
+/* CTAs topo_sccn_combine_fwd_tc2 / topo_sccn_combine_bwd_tc launch for `rows` rows under the max_ctas bound of topo_combine_params */
+int topo_sccn_combine_grid(int64_t rows, int max_ctas);
 
 int topo_sccn_combine_fwd(const topo_combine_params* p, int64_t rows, const int32_t* n_rows_dev,
                           float* out, topo_stream_t stream);

@@ -48,14 +48,19 @@ WEIGHT_IMAGE_BYTES = 24576
 
 class WgradJob(C.Structure):
     """topo_wgrad_job"""
-    _fields_ = [("wprod", C.c_void_p), ("w", C.c_void_p), ("scale", C.c_void_p), ("g_w", C.c_void_p), ("g_scale", C.c_void_p)]
+    _fields_ = [("wprod", C.c_void_p), ("w", C.c_void_p), ("scale", C.c_void_p), ("g_w", C.c_void_p), ("g_scale", C.c_void_p),
+                ("partials", C.c_void_p), ("n_rows_dev", C.c_void_p), ("rows", C.c_int64), ("partial_offset", C.c_int32),
+                ("count", C.c_int32), ("max_ctas", C.c_int32), ("reserved_", C.c_int32)]
 
 
 class CombineGrads(C.Structure):
     """topo_combine_grads"""
     _fields_ = [("g_agg", C.c_void_p * 3), ("g_x", C.c_void_p), ("g_wprod", C.c_void_p * 3),
                 ("g_att_w1", C.c_void_p), ("g_att_b1", C.c_void_p), ("g_att_w2", C.c_void_p),
-                ("g_att_b2", C.c_void_p), ("g_ln_gamma", C.c_void_p), ("g_ln_beta", C.c_void_p)]
+                ("g_att_b2", C.c_void_p), ("g_ln_gamma", C.c_void_p), ("g_ln_beta", C.c_void_p), ("cta_partials", C.c_void_p)]
+
+
+CTA_PARTIAL_FLOATS = 16704          # TOPO_CTA_PARTIAL_FLOATS
 
 
 _P, _I64, _I32, _F = C.c_void_p, C.c_int64, C.c_int, C.c_float
@@ -95,6 +100,7 @@ SIGNATURES = {
     "topo_sddmm_csr": [_I64, _P, _P, _P, _P, _I32, _P, _P],
     "topo_sccn_prepare_images": [C.POINTER(ImageJob), _I32, _I32, _P],
     "topo_sccn_finish_weight_grads": [C.POINTER(WgradJob), _I32, _I32, _P],
+    "topo_sccn_combine_grid": [_I64, _I32],
     "topo_sccn_combine_fwd": [C.POINTER(CombineParams), _I64, _P, _P, _P],
     "topo_sccn_combine_fwd_tc": [C.POINTER(CombineParams), _I64, _P, _P, _P],
     "topo_sccn_combine_fwd_tc2": [C.POINTER(CombineParams), _I64, _P, _P, _P],
@@ -116,7 +122,8 @@ SIGNATURES = {
 _NON_STATUS = {"topo_version": C.c_int, "topo_last_error": C.c_char_p, "topo_tables_destroy": None,
                "topo_debug_fwd16_mask": None, "topo_debug_fwd16_stamps": None, "topo_debug_bwd_stamps": None,
                "topo_distance_padded_size": C.c_int64, "topo_distance_image_bytes": C.c_int64,
-               "topo_distance_workspace_floats": C.c_int64, "topo_distance_logq_words": C.c_int64}
+               "topo_distance_workspace_floats": C.c_int64, "topo_distance_logq_words": C.c_int64,
+               "topo_sccn_combine_grid": C.c_int}
 
 # unit-test / measurement entry points: only in libtopo_b200_debug.so (csrc/build.py build_debug()), never in the product library
 DEBUG_LIB_PATH = os.path.join(_HERE, "libtopo_b200_debug.so")

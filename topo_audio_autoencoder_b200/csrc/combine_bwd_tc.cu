@@ -15,7 +15,8 @@
 //   g_x = sum_k dm_k.  The GELU' of message k + 1 is evaluated while round 2 of message k runs.
 // DW1 and DWp_k (64 x 64 each) stay in tensor memory for the whole CTA and are added to global memory once
 // (red.global.add.v4.f32).  The row-contraction MMAs are issued with M = 64 (accumulator row i in TMEM lane
-// 32 (i / 16) + i % 16), three threads share the 72 MMAs of a round.
+// 32 (i / 16) + i % 16); the 72 MMAs of a round are issued by two or three threads, ONE per accumulator (the order in which
+// the tensor pipe adds into an accumulator is then fixed: with per-CTA partial sums the parameter gradients are bit-reproducible).
 // Column sums (b1, w2, gamma, beta gradients) accumulate in the chunk map's registers (eight columns per thread) and
 // meet once per CTA: two shuffles per value, one pass through shared memory, one atomic per column.
 // Every global load is issued at least one phase before its first use (phase-A operands of the next tile before the
@@ -179,11 +180,17 @@ __global__ void __launch_bounds__(kThreads, 1) combine_bwd_fused_kernel(topo_com
     const int q = tid >> 7, r = tid & 127, col0 = q * kCW;     // row map
     const int c = tid & 7, ra = tid >> 3;                       // chunk map: rows ra and ra + 64
     constexpr int n_msgs = NM;
+    // The tensor pipe adds the MMAs of DIFFERENT issuing threads into one accumulator in an order that varies from run to run,
+    // so every weight-gradient accumulator belongs to ONE issuing thread.  With up to two messages the two halves of a row
+    // contraction (tile rows 0-63 and 64-127) get an accumulator each -- three issuing threads, all 512 columns used -- and are
+    // added when the CTA flushes; with three messages tensor memory has no room for that and one thread issues both halves.
+    constexpr bool kSplit = NM <= 2;
+    constexpr uint32_t kSecondHalf = kSplit ? 64u * (1 + NM) : 0u;       // column offset of the second-half accumulators
     const bool apply_ln = P.apply_ln != 0;
     const bool tf = P.saved_layout == TOPO_SAVED_TILE_FRAGMENT;
 
     if (tid == 0) {
-        mbar_init(bar, 3);            // three issuing threads commit every round
+        mbar_init(bar, kSplit ? 3 : 2);          // the issuing threads commit every round
         fence_barrier_init();
     }
     if (warp == 0) tmem_alloc(tmem_base_smem, 512);
@@ -211,7 +218,7 @@ __global__ void __launch_bounds__(kThreads, 1) combine_bwd_fused_kernel(topo_com
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_base_smem;
-    // tensor-memory columns: T | Ga | DW1 | DWp_0 | DWp_1 | DWp_2
+    // tensor-memory columns: T | Ga | DW1 | DWp_0 .. DWp_{NM-1} [| the same again for tile rows 64-127 when kSplit]
     const uint32_t tm_t = tmem_base, tm_ga = tmem_base + 64, tm_dw1 = tmem_base + 128, tm_dwp = tmem_base + 192;
     const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
     {
@@ -219,6 +226,10 @@ __global__ void __launch_bounds__(kThreads, 1) combine_bwd_fused_kernel(topo_com
         const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int c8 = 0; c8 < 8; ++c8) tmem_st8(tm_dw1 + lane_addr + q * 64 + c8 * 8, z);
+        if (kSplit && NM == 2 && q < 2) {
+#pragma unroll
+            for (int c8 = 0; c8 < 8; ++c8) tmem_st8(tm_dw1 + lane_addr + 256 + q * 64 + c8 * 8, z);
+        }
         tmem_st_wait();
         tc_fence_before_sync();
         __syncthreads();
@@ -456,16 +467,18 @@ __global__ void __launch_bounds__(kThreads, 1) combine_bwd_fused_kernel(topo_com
             tc_fence_before_sync();
             __syncthreads();
             stamp();                                           // barrier 1 passed
-            if (warp < 3) {
-                // three issuing threads share the 72 MMAs of the round (issue rate, not the tensor pipe, bounds a round)
+            if (warp < (kSplit ? 3 : 2)) {
+                // one issuing thread per accumulator: the 24 MMAs of the row product, the 48 of the row contraction in one or two halves
                 if (lane == 0) {
                     tc_fence_after_sync();
                     if (warp == 0)
                         gemm_bf16x3_unrolled<kC / 16>(tm_t, k_major(p_s, kTileRows), mn_major(w1_s, kC, kWPart), idesc_bf16(128, 64, 0, 1), 0);
+                    else if (!kSplit)
+                        gemm_bf16x3_unrolled<8, 0>(tm_dw1, mn_major(p_s, kTileRows, kPart), mn_major(q_s, kTileRows, kPart), idesc_bf16(64, 64, 1, 1), 1);
                     else if (warp == 1)
                         gemm_bf16x3_unrolled<4, 0>(tm_dw1, mn_major(p_s, kTileRows, kPart), mn_major(q_s, kTileRows, kPart), idesc_bf16(64, 64, 1, 1), 1);
                     else
-                        gemm_bf16x3_unrolled<4, 4>(tm_dw1, mn_major(p_s, kTileRows, kPart), mn_major(q_s, kTileRows, kPart), idesc_bf16(64, 64, 1, 1), 1);
+                        gemm_bf16x3_unrolled<4, 4>(tm_dw1 + kSecondHalf, mn_major(p_s, kTileRows, kPart), mn_major(q_s, kTileRows, kPart), idesc_bf16(64, 64, 1, 1), 1);
                     mma_commit(bar);
                 }
                 __syncwarp();      // the other lanes park here instead of polling against the issuing lane
@@ -516,15 +529,17 @@ __global__ void __launch_bounds__(kThreads, 1) combine_bwd_fused_kernel(topo_com
             fence_async_shared();
             tc_fence_before_sync();
             __syncthreads();
-            if (warp < 3) {
+            if (warp < (kSplit ? 3 : 2)) {
                 if (lane == 0) {
                     tc_fence_after_sync();
                     if (warp == 0)
                         gemm_bf16x3_unrolled<kC / 16>(tm_ga, k_major(p_s, kTileRows), k_major(wk_s + k * kWImg, kC), idesc_bf16(128, 64, 0, 0), 0);
+                    else if (!kSplit)
+                        gemm_bf16x3_unrolled<8, 0>(tm_dwp + k * 64, mn_major(q_s, kTileRows, kPart), mn_major(p_s, kTileRows, kPart), idesc_bf16(64, 64, 1, 1), 1);
                     else if (warp == 1)
                         gemm_bf16x3_unrolled<4, 0>(tm_dwp + k * 64, mn_major(q_s, kTileRows, kPart), mn_major(p_s, kTileRows, kPart), idesc_bf16(64, 64, 1, 1), 1);
                     else
-                        gemm_bf16x3_unrolled<4, 4>(tm_dwp + k * 64, mn_major(q_s, kTileRows, kPart), mn_major(p_s, kTileRows, kPart), idesc_bf16(64, 64, 1, 1), 1);
+                        gemm_bf16x3_unrolled<4, 4>(tm_dwp + k * 64 + kSecondHalf, mn_major(q_s, kTileRows, kPart), mn_major(p_s, kTileRows, kPart), idesc_bf16(64, 64, 1, 1), 1);
                     mma_commit(bar);
                 }
                 __syncwarp();
@@ -578,31 +593,69 @@ __global__ void __launch_bounds__(kThreads, 1) combine_bwd_fused_kernel(topo_com
                 part[(warp * 4 + 3) * kC + 8 * c + i] = p_beta[i];
             }
         }
+        p_b2 = warp_sum(p_b2);
+        if (lane == 0) part[(kThreads / 32) * 4 * kC + warp] = p_b2;
         __syncthreads();
+        // with a partials buffer this CTA's sums go to its own slot with plain stores (topo_sccn_finish_weight_grads adds the
+        // slots in CTA order: bit-reproducible); without one they are added to the shared accumulators atomically
+        float* slot = G.cta_partials != nullptr ? G.cta_partials + static_cast<size_t>(blockIdx.x) * kCtaPartialFloats : nullptr;
         if (tid < 4 * kC) {
             const int which = tid >> 6, col = tid & 63;
             float sum = 0.f;
 #pragma unroll
             for (int w = 0; w < kThreads / 32; ++w) sum += part[(w * 4 + which) * kC + col];
-            float* dst = which == 0 ? G.g_att_b1 : (which == 1 ? G.g_att_w2 : (which == 2 ? G.g_ln_gamma : G.g_ln_beta));
-            if (which < 2 || apply_ln) atomicAdd(dst + col, sum);
+            if (slot != nullptr) {
+                slot[4 * kC * kC + which * kC + col] = sum;      // b1, w2, gamma, beta
+            } else {
+                float* dst = which == 0 ? G.g_att_b1 : (which == 1 ? G.g_att_w2 : (which == 2 ? G.g_ln_gamma : G.g_ln_beta));
+                if (which < 2 || apply_ln) atomicAdd(dst + col, sum);
+            }
+        } else if (tid == 4 * kC) {
+            float sum = 0.f;
+#pragma unroll
+            for (int w = 0; w < kThreads / 32; ++w) sum += part[(kThreads / 32) * 4 * kC + w];
+            if (slot != nullptr) slot[4 * kC * kC + 4 * kC] = sum;
+            else if (sum != 0.f) atomicAdd(G.g_att_b2, sum);
         }
     }
-    p_b2 = warp_sum(p_b2);
-    if (lane == 0 && p_b2 != 0.f) atomicAdd(G.g_att_b2, p_b2);
     {
         // M = 64 accumulators: row i lives in lane 32 (i / 16) + i % 16, i.e. lanes 0..15 of every lane quarter;
         // warp group g = warp / 4 drains DW1 (g = 0) or DWp_{g-1}
         const int g = warp >> 2;
         const int drow = (warp & 3) * 16 + (lane & 15);
+        float* slot = G.cta_partials != nullptr ? G.cta_partials + static_cast<size_t>(blockIdx.x) * kCtaPartialFloats + g * kC * kC : nullptr;
         float* dst = g == 0 ? G.g_att_w1 : (g - 1 < n_msgs ? G.g_wprod[g - 1] : nullptr);
-        if (dst != nullptr) {
+        if (slot != nullptr && (g == 0 || g - 1 < n_msgs)) {
+            const uint32_t src = (g == 0 ? tm_dw1 : tm_dwp + (g - 1) * 64) + lane_addr;
+#pragma unroll 1
+            for (int c8 = 0; c8 < 8; ++c8) {
+                float v[8];
+                tmem_ld8(src + c8 * 8, v);
+                if (kSplit) {
+                    float v2[8];
+                    tmem_ld8(src + kSecondHalf + c8 * 8, v2);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[i] += v2[i];
+                }
+                if (lane < 16) {
+                    float4* d8 = reinterpret_cast<float4*>(slot + drow * kC + c8 * 8);      // slots are 16-byte aligned (16704 floats apart)
+                    d8[0] = make_float4(v[0], v[1], v[2], v[3]);
+                    d8[1] = make_float4(v[4], v[5], v[6], v[7]);
+                }
+            }
+        } else if (dst != nullptr) {
             const bool vec_ok = (reinterpret_cast<uintptr_t>(dst) & 15) == 0;
             const uint32_t src = (g == 0 ? tm_dw1 : tm_dwp + (g - 1) * 64) + lane_addr;
 #pragma unroll 1
             for (int c8 = 0; c8 < 8; ++c8) {
                 float v[8];
                 tmem_ld8(src + c8 * 8, v);
+                if (kSplit) {
+                    float v2[8];
+                    tmem_ld8(src + kSecondHalf + c8 * 8, v2);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[i] += v2[i];
+                }
                 if (lane < 16) {
                     float* d8 = dst + drow * kC + c8 * 8;
                     if (vec_ok) {                          // 16-byte aligned accumulators: two 4-wide reductions
@@ -642,14 +695,16 @@ extern "C" int topo_sccn_combine_bwd_tc(const topo_combine_params* p, int64_t ro
     }
     TOPO_REQUIRE(p->saved_score, "the fused backward needs the forward's saved scores");
     for (int k = 0; k < p->n_msgs; ++k)
-        TOPO_REQUIRE(p->agg[k] && p->w[k] && p->scale[k] && p->saved_m[k] && p->saved_pre[k] && g->g_agg[k] && g->g_wprod[k],
+        TOPO_REQUIRE(p->agg[k] && p->w[k] && p->scale[k] && p->saved_m[k] && p->saved_pre[k] && g->g_agg[k] &&
+                         (g->g_wprod[k] || g->cta_partials),
                      "null message operand (the fused backward needs the forward's saved activations)");
-    TOPO_REQUIRE(p->att_w1 && p->att_w2 && g->g_att_w1 && g->g_att_b1 && g->g_att_w2 && g->g_att_b2, "null attention parameter");
-    TOPO_REQUIRE(!p->apply_ln || (p->ln_gamma && g->g_ln_gamma && g->g_ln_beta), "null LayerNorm parameter");
+    TOPO_REQUIRE(p->att_w1 && p->att_w2 && (g->cta_partials || (g->g_att_w1 && g->g_att_b1 && g->g_att_w2 && g->g_att_b2)),
+                 "null attention parameter");
+    TOPO_REQUIRE(!p->apply_ln || (p->ln_gamma && (g->cta_partials || (g->g_ln_gamma && g->g_ln_beta))), "null LayerNorm parameter");
+    TOPO_REQUIRE((reinterpret_cast<uintptr_t>(g->cta_partials) & 15) == 0, "cta_partials must be 16-byte aligned");
     if (rows == 0) return TOPO_OK;
     const size_t smem = BwdSmem::kTotal;
-    const int tiles = static_cast<int>((rows + kTileRows - 1) / kTileRows);
-    const int grid = std::min(tiles, p->max_ctas > 0 ? std::min(p->max_ctas, sm_count()) : sm_count());
+    const int grid = combine_grid(rows, p->max_ctas);
 #define TOPO_LAUNCH_BWD(NM)                                                                                                  \
     do {                                                                                                                     \
         if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(combine_bwd_fused_kernel<NM>), smem)) return rc;      \

@@ -535,8 +535,7 @@ extern "C" int topo_sccn_combine_fwd_tc2(const topo_combine_params* p, int64_t r
     if (rows == 0) return TOPO_OK;
     const size_t smem = FwdSmem16::kTotal;
     if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(combine_fwd16_kernel), smem)) return rc;
-    const int tiles = static_cast<int>((rows + kTileRows - 1) / kTileRows);
-    combine_fwd16_kernel<<<std::min(tiles, p->max_ctas > 0 ? std::min(p->max_ctas, sm_count()) : sm_count()), kThreads, smem, as_stream(stream)>>>(*p, rows, n_rows_dev, out, g_fwd16_debug_mask, g_fwd16_stamps);
+    combine_fwd16_kernel<<<combine_grid(rows, p->max_ctas), kThreads, smem, as_stream(stream)>>>(*p, rows, n_rows_dev, out, g_fwd16_debug_mask, g_fwd16_stamps);
     TOPO_LAUNCH_CHECK();
     return TOPO_OK;
 }

@@ -37,6 +37,13 @@ static inline cudaStream_t as_stream(topo_stream_t s) { return reinterpret_cast<
 int sm_count();
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per kernel (never again, e.g. not inside a graph capture)
 int ensure_dynamic_smem(const void* kernel, size_t bytes);
+// CTAs of a tensor-core combine launch (128-row tiles, persistent CTAs, at most one per SM and at most max_ctas when set)
+inline int combine_grid(int64_t rows, int max_ctas) {
+    const int64_t tiles = (rows + 127) / 128;
+    const int cap = max_ctas > 0 ? (max_ctas < sm_count() ? max_ctas : sm_count()) : sm_count();
+    return static_cast<int>(tiles < cap ? tiles : cap);
+}
+constexpr int kCtaPartialFloats = 16704;      // TOPO_CTA_PARTIAL_FLOATS: [w1][wprod x 3] 4 x 4096, [b1][w2][gamma][beta] 4 x 64, [b2] 1 (+ 63)
 
 constexpr int kMaxRank = 3;
 

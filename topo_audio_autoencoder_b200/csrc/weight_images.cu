@@ -70,18 +70,51 @@ struct WgradJobs {
     topo_wgrad_job j[kMaxJobs];
 };
 
-__global__ void __launch_bounds__(256) finish_weight_grads_kernel(const __grid_constant__ WgradJobs jobs, int n) {
+// One CTA of 1024 threads per job.  Elements are taken 256 at a time; with a partials buffer the four thread quarters each add
+// every fourth CTA slot of an element (independent loads, fixed order) and meet in shared memory, again in a fixed order.
+__global__ void __launch_bounds__(1024) finish_weight_grads_kernel(const __grid_constant__ WgradJobs jobs, int n_default, int grid_cap) {
+    __shared__ float quarter[4][256];
     __shared__ float part[8];
     const topo_wgrad_job job = jobs.j[blockIdx.x];
-    const float s = __ldg(job.scale);
-    float acc = 0.f;
-    for (int i = threadIdx.x; i < n; i += 256) {
-        const float p = job.wprod[i];
-        job.g_w[i] = s * p;
-        acc = fmaf(p, __ldg(job.w + i), acc);
+    const int n = job.count > 0 ? job.count : n_default;
+    const int e = threadIdx.x & 255, qd = threadIdx.x >> 8;
+    const bool conv = job.w != nullptr;
+    const float s = conv ? __ldg(job.scale) : 1.f;
+    int n_active = 0;
+    if (job.partials != nullptr) {
+        const long long live = job.n_rows_dev ? min(static_cast<long long>(*job.n_rows_dev), static_cast<long long>(job.rows)) : job.rows;
+        const long long tiles = (live + 127) / 128, launched = (job.rows + 127) / 128;
+        const int cap = job.max_ctas > 0 ? min(job.max_ctas, grid_cap) : grid_cap;
+        n_active = static_cast<int>(min(tiles, min(launched, static_cast<long long>(cap))));
     }
-    acc = warp_sum(acc);
-    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+    float acc = 0.f;
+    for (int i0 = 0; i0 < n; i0 += 256) {
+        const int i = i0 + e;
+        float p = 0.f;
+        if (job.partials != nullptr) {
+            float t = 0.f;
+            if (i < n) {
+                const float* src = job.partials + job.partial_offset + i;
+#pragma unroll 4
+                for (int b = qd; b < n_active; b += 4) t += __ldcs(src + static_cast<size_t>(b) * kCtaPartialFloats);
+            }
+            quarter[qd][e] = t;
+            __syncthreads();
+            p = (quarter[0][e] + quarter[1][e]) + (quarter[2][e] + quarter[3][e]);
+            __syncthreads();
+        } else if (i < n) {
+            p = job.wprod[i];
+        }
+        if (qd == 0 && i < n) {
+            job.g_w[i] = s * p;
+            if (conv) acc = fmaf(p, __ldg(job.w + i), acc);
+        }
+    }
+    if (!conv) return;
+    if (qd == 0) {
+        acc = warp_sum(acc);
+        if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
         float t = 0.f;
@@ -100,13 +133,18 @@ extern "C" int topo_sccn_finish_weight_grads(const topo_wgrad_job* jobs, int n_j
     if (n_jobs == 0) return TOPO_OK;
     WgradJobs packed{};
     for (int q = 0; q < n_jobs; ++q) {
-        TOPO_REQUIRE(jobs[q].wprod && jobs[q].w && jobs[q].scale && jobs[q].g_w && jobs[q].g_scale, "null pointer in a weight-gradient job");
+        TOPO_REQUIRE((jobs[q].wprod || jobs[q].partials) && jobs[q].g_w, "null pointer in a weight-gradient job");
+        TOPO_REQUIRE(jobs[q].w == nullptr || (jobs[q].scale && jobs[q].g_scale), "a conv-weight job needs scale and g_scale");
+        TOPO_REQUIRE(jobs[q].count >= 0 && jobs[q].partial_offset >= 0 && jobs[q].partial_offset + jobs[q].count <= kCtaPartialFloats &&
+                         jobs[q].rows >= 0, "bad partials geometry in a weight-gradient job");
         packed.j[q] = jobs[q];
     }
-    finish_weight_grads_kernel<<<n_jobs, 256, 0, as_stream(stream)>>>(packed, channels * channels);
+    finish_weight_grads_kernel<<<n_jobs, 1024, 0, as_stream(stream)>>>(packed, channels * channels, sm_count());
     TOPO_LAUNCH_CHECK();
     return TOPO_OK;
 }
+
+extern "C" int topo_sccn_combine_grid(int64_t rows, int max_ctas) { return rows > 0 ? combine_grid(rows, max_ctas) : 0; }
 
 extern "C" int topo_sccn_prepare_images(const topo_image_job* jobs, int n_jobs, int channels, topo_stream_t stream) {
     TOPO_REQUIRE(jobs && n_jobs >= 0 && n_jobs <= kMaxJobs, "at most 96 jobs per call");

@@ -26,7 +26,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from ._lib import (lib, check, ptr, ptr_array, stream, ComplexView, CombineParams, CombineGrads, ImageJob, WgradJob,
+from ._lib import (lib, check, ptr, ptr_array, stream, ComplexView, CombineParams, CombineGrads, ImageJob, WgradJob, CTA_PARTIAL_FLOATS,
                    WEIGHT_IMAGE_BYTES)
 from .rectifier import _Tables
 
@@ -210,6 +210,12 @@ def _side_streams(device: torch.device) -> List[torch.cuda.Stream]:
     return _SIDE_STREAMS[idx]
 
 
+BWD_THREE_MESSAGE_COST = float(os.environ.get("TOPO_BWD_NM3_COST", "1.15"))
+BWD_FIXED_COST = float(os.environ.get("TOPO_BWD_FIXED_COST", "1.2"))
+FWD_FIXED_COST = float(os.environ.get("TOPO_FWD_FIXED_COST", "1.2"))
+FWD_THREE_MESSAGE_COST = float(os.environ.get("TOPO_FWD_NM3_COST", "1.0"))
+
+
 def _sm_shares(costs: Sequence[float], n_sm: int, units: Optional[Sequence[int]] = None) -> List[int]:
     """Split the SMs between concurrent persistent launches so that they finish together.
 
@@ -316,8 +322,14 @@ class _LayerCombineFn(torch.autograd.Function):
         n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
         tiles = [max(1, int(-(-pr["aggs"][0].shape[0] * ROW_FRACTION_HINT[r] // 128))) if pr["aggs"][0].shape[0] else 0
                  for r, pr in enumerate(per)]
-        costs = [t * (rc["n_msgs"] + 1.2) for t, rc in zip(tiles, ranks)]       # per tile: a fixed part + one part per message
+        # per tile: a fixed part + one part per message
+        costs = [t * (rc["n_msgs"] + FWD_FIXED_COST) * (FWD_THREE_MESSAGE_COST if rc["n_msgs"] == 3 else 1.0) for t, rc in zip(tiles, ranks)]
         shares = _sm_shares(costs, n_sm, tiles)
+        # the backward of a three-message rank issues both halves of its row contractions from one thread (tensor memory has no
+        # room for per-half accumulators there, and an accumulator must have ONE issuing thread to be reproducible): its tiles
+        # cost a little more than the forward's ratio says
+        ctx.shares_bwd = _sm_shares([t * (rc["n_msgs"] + BWD_FIXED_COST) * (BWD_THREE_MESSAGE_COST if rc["n_msgs"] == 3 else 1.0)
+                                     for t, rc in zip(tiles, ranks)], n_sm, tiles)
         outs = []
         for pr, rc in zip(per, ranks):
             rows = pr["aggs"][0].shape[0]
@@ -346,30 +358,33 @@ class _LayerCombineFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, *g_outs):
-        per, ranks, shares, order = ctx.per, ctx.ranks, ctx.shares, ctx.order
+        per, ranks, shares, order = ctx.per, ctx.ranks, ctx.shares_bwd, ctx.order
         dev = per[0]["aggs"][0].device
         ch = per[0]["aggs"][0].shape[1]
-        # one zero fill for everything the kernels accumulate into: per rank [wprod x n | w1 | b1 | w2 | b2 | gamma | beta]
-        sizes = [rc["n_msgs"] * ch * ch + ch * ch + 3 * ch + 1 + ch for rc in ranks]        # (+ ch: padding keeps 16-byte alignment)
-        sizes = [-(-sz // 4) * 4 for sz in sizes]
-        acc = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
+        # parameter gradients: every CTA of a rank's launch stores its partial sums in its own slot of `partials[i]`
+        # (plain stores) and ONE launch adds the slots in CTA order afterwards (topo_sccn_finish_weight_grads): no
+        # floating-point atomics, bit-reproducible.  `acc` receives the results: per rank [w1 | b1 | w2 | gamma | beta | b2].
+        sizes = [ch * ch + 4 * ch + 4 for rc in ranks]
+        acc = torch.empty(sum(sizes), dtype=torch.float32, device=dev)
         grads_flat = [None] * ctx.n_flat
         forked = _Forked(dev, order)
         keep, jobs = [], []
         off = 0
         views = []
+        partials = []
         for i, (pr, rc) in enumerate(zip(per, ranks)):
-            n, base = rc["n_msgs"], off
-            v = {"wprod": [acc[base + k * ch * ch: base + (k + 1) * ch * ch].view(ch, ch) for k in range(n)]}
-            base += n * ch * ch
-            v["w1"] = acc[base:base + ch * ch].view(ch, ch); base += ch * ch
-            v["b1"] = acc[base:base + ch]; base += ch
+            base = off
+            v = {"w1": acc[base:base + ch * ch].view(ch, ch)}
+            base += ch * ch
+            v["b1"] = acc[base:base + ch]; base += ch          # b1, w2, gamma, beta, b2: the order of a CTA slot's tail
             v["w2"] = acc[base:base + ch]; base += ch
             v["gamma"] = acc[base:base + ch]; base += ch
             v["beta"] = acc[base:base + ch]; base += ch
             v["b2"] = acc[base:base + 1]
             views.append(v)
             off += sizes[i]
+            slots = int(lib.topo_sccn_combine_grid(pr["aggs"][0].shape[0], shares[i]))
+            partials.append(torch.empty(max(slots, 1) * CTA_PARTIAL_FLOATS, dtype=torch.float32, device=dev))
         for position, i in enumerate(order):
             pr, rc, v = per[i], ranks[i], views[i]
             rows, n = pr["aggs"][0].shape[0], rc["n_msgs"]
@@ -390,28 +405,43 @@ class _LayerCombineFn(torch.autograd.Function):
             grads = CombineGrads()
             for k in range(3):
                 grads.g_agg[k] = ptr(g_aggs[k]) if k < n else None
-                grads.g_wprod[k] = ptr(v["wprod"][k]) if k < n else None
             grads.g_x = ptr(g_x)
-            grads.g_att_w1, grads.g_att_b1 = ptr(v["w1"]), ptr(v["b1"])
-            grads.g_att_w2, grads.g_att_b2 = ptr(v["w2"]), ptr(v["b2"])
-            grads.g_ln_gamma, grads.g_ln_beta = ptr(v["gamma"]), ptr(v["beta"])
+            grads.cta_partials = ptr(partials[i])
             check(lib.topo_sccn_combine_bwd_tc(C.byref(params), rows, ptr(rc["n_rows_dev"], torch.int32), ptr(g_out),
                                                C.byref(grads), forked.stream_for(position)))
         forked.join()
-        # conv-weight chain tail for every message of the layer in one launch: dW_k = s_k P_k, ds_k = <W_k, P_k>
+        # the ordered sum over the CTA slots for every parameter of the layer in one launch, with the conv-weight chain's tail
+        # on top of it: P_k = sum of slots, dW_k = s_k P_k, ds_k = <W_k, P_k>
         n_total = sum(rc["n_msgs"] for rc in ranks)
         g_w_all = torch.empty(n_total, ch, ch, dtype=torch.float32, device=dev)
         g_s_all = torch.empty(n_total, dtype=torch.float32, device=dev)
-        arr = (WgradJob * n_total)()
-        q = 0
+        arr = (WgradJob * (n_total + 2 * len(ranks)))()
+        q = m = 0          # job number, message number
+
+        def _slots(job, i, offset, count):
+            pr, rc = per[i], ranks[i]
+            rows = pr["aggs"][0].shape[0]
+            launched = rows > 0 and g_outs[i] is not None
+            job.partials, job.partial_offset, job.count = ptr(partials[i]), offset, count
+            job.n_rows_dev, job.rows, job.max_ctas = ptr(rc["n_rows_dev"], torch.int32), (rows if launched else 0), shares[i]
+
         for i, (pr, rc) in enumerate(zip(per, ranks)):
             for k in range(rc["n_msgs"]):
-                arr[q].wprod, arr[q].w, arr[q].scale = ptr(views[i]["wprod"][k]), ptr(pr["ws"][k]), ptr(pr["scales"][k])
-                arr[q].g_w, arr[q].g_scale = g_w_all[q].data_ptr(), g_s_all[q:q + 1].data_ptr()
+                arr[q].w, arr[q].scale = ptr(pr["ws"][k]), ptr(pr["scales"][k])
+                arr[q].g_w, arr[q].g_scale = g_w_all[m].data_ptr(), g_s_all[m:m + 1].data_ptr()
+                _slots(arr[q], i, (1 + k) * ch * ch, ch * ch)
                 q += 1
+                m += 1
+            arr[q].g_w = ptr(views[i]["w1"])
+            _slots(arr[q], i, 0, ch * ch)
+            q += 1
+            arr[q].g_w = ptr(views[i]["b1"])                     # b1, w2, gamma, beta, b2 are contiguous on both sides
+            _slots(arr[q], i, 4 * ch * ch, 4 * ch + 1)
+            q += 1
+        n_jobs = q
         # ... on a side stream: the aggregation backward below does not depend on it
         tail = _Forked(dev, None)
-        check(lib.topo_sccn_finish_weight_grads(arr, n_total, ch, tail.stream_for(1) if ctx.agg is not None else stream()))
+        check(lib.topo_sccn_finish_weight_grads(arr, n_jobs, ch, tail.stream_for(1) if ctx.agg is not None else stream()))
         agg = ctx.agg
         if agg is not None:
             # the aggregation backward runs on this node's own buffers: it updates g_down[2], g_up[2], g_up[3] in
