@@ -70,7 +70,9 @@ int topo_tables_face_matrix(const topo_tables* t, int rank, float* dev_out, topo
  *   x = logits + loc[rank];  training: x = (log u - log(1-u) + x) / beta
  *   s = sigmoid(x);  z = clamp(s*(zeta-gamma)+gamma, 0, 1);  ste: value (z > 0.5), gradient of z
  * params = device float[7] {beta, gamma, zeta, loc0, loc1, loc2, loc3}.  128-bit vectorised.
- * grad_params (device float[7]) is overwritten.  u may be NULL when training == 0.
+ * grad_params (device float[7]) is overwritten.  u may be NULL when training == 0.  bwd workspace: NULL (the seven sums are
+ * accumulated with floating-point atomics) or topo_hard_concrete_bwd_workspace_floats floats (per-CTA sums added in CTA order:
+ * bit-reproducible).
  * Binary Gumbel: BinaryGumbel.forward training branch (encoder.py:34-41),
  *   softmax(([l, 1-l] + g) / temp, dim 0)[0] with g = dev_gumbels [2, count].
  * ------------------------------------------------------------------------------------------- */
@@ -80,7 +82,8 @@ int topo_hard_concrete_fwd(const float* logits, const float* u, const float* par
 int topo_hard_concrete_bwd(const float* logits, const float* u, const float* params,
                            const int64_t host_offsets[5], int64_t batch, int training,
                            const float* grad_z, float* grad_logits, float* grad_params,
-                           topo_stream_t stream);
+                           float* workspace, topo_stream_t stream);
+int64_t topo_hard_concrete_bwd_workspace_floats(const int64_t host_offsets[5], int64_t batch);
 int topo_binary_gumbel_fwd(const float* logits, const float* gumbels, float temp, int64_t count,
                            float* probs, topo_stream_t stream);
 int topo_binary_gumbel_bwd(const float* logits, const float* gumbels, float temp, int64_t count,
@@ -145,12 +148,14 @@ int topo_embed_bwd(const topo_tables* t, const topo_complex_view* cv, int rank, 
                    topo_stream_t stream);
 
 /* Row-wise LayerNorm over [rows, channels] (nn.LayerNorm, eps inside the sqrt, biased variance).
- * bwd overwrites grad_x and ACCUMULATES into grad_gamma / grad_beta. */
+ * bwd overwrites grad_x and ACCUMULATES into grad_gamma / grad_beta: with floating-point atomics when workspace is NULL, from
+ * per-CTA column sums added in CTA order (bit-reproducible) when it holds topo_layernorm_bwd_workspace_floats floats. */
 int topo_layernorm_fwd(int64_t rows, int channels, const float* x, const float* gamma,
                        const float* beta, float eps, float* y, topo_stream_t stream);
 int topo_layernorm_bwd(int64_t rows, int channels, const float* x, const float* gamma, float eps,
                        const float* grad_y, float* grad_x, float* grad_gamma, float* grad_beta,
-                       topo_stream_t stream);
+                       float* workspace, topo_stream_t stream);
+int64_t topo_layernorm_bwd_workspace_floats(int64_t rows, int channels);
 
 /* ---------------------------------------------------------------------------------------------
  * B2. Weighted incidence / adjacency operators.  Replaces build_sparse_matrices

@@ -79,7 +79,8 @@ SIGNATURES = {
     "topo_tables_cofaces": [_P, _I32, _P],
     "topo_tables_face_matrix": [_P, _I32, _P, _P],
     "topo_hard_concrete_fwd": [_P, _P, _P, C.POINTER(_I64), _I64, _I32, _I32, _P, _P],
-    "topo_hard_concrete_bwd": [_P, _P, _P, C.POINTER(_I64), _I64, _I32, _P, _P, _P, _P],
+    "topo_hard_concrete_bwd": [_P, _P, _P, C.POINTER(_I64), _I64, _I32, _P, _P, _P, _P, _P],
+    "topo_hard_concrete_bwd_workspace_floats": [C.POINTER(_I64), _I64],
     "topo_binary_gumbel_fwd": [_P, _P, _F, _I64, _P, _P],
     "topo_binary_gumbel_bwd": [_P, _P, _F, _I64, _P, _P, _P],
     "topo_rectify_fwd": [_P, _P, _F, _I64, _P, _P],
@@ -90,7 +91,8 @@ SIGNATURES = {
     "topo_embed_fwd": [_P, C.POINTER(ComplexView), _I32, _I32, _P, _P, _P],
     "topo_embed_bwd": [_P, C.POINTER(ComplexView), _I32, _I32, _P, _P, _P, _P, _P],
     "topo_layernorm_fwd": [_I64, _I32, _P, _P, _P, _F, _P, _P],
-    "topo_layernorm_bwd": [_I64, _I32, _P, _P, _F, _P, _P, _P, _P, _P],
+    "topo_layernorm_bwd": [_I64, _I32, _P, _P, _F, _P, _P, _P, _P, _P, _P],
+    "topo_layernorm_bwd_workspace_floats": [_I64, _I32],
     "topo_operators_count": [_P, _P, _P, _P, _P, _I64, _P, _P],
     "topo_operators_fill": [_P, _P, _P, _P, _P, _I64, _P, _PP, _PP, _PP, _P],
     "topo_operators_bwd": [_P, _P, _P, _P, _P, _I64, _P, _PP, _P, _P],
@@ -123,7 +125,8 @@ _NON_STATUS = {"topo_version": C.c_int, "topo_last_error": C.c_char_p, "topo_tab
                "topo_debug_fwd16_mask": None, "topo_debug_fwd16_stamps": None, "topo_debug_bwd_stamps": None,
                "topo_distance_padded_size": C.c_int64, "topo_distance_image_bytes": C.c_int64,
                "topo_distance_workspace_floats": C.c_int64, "topo_distance_logq_words": C.c_int64,
-               "topo_sccn_combine_grid": C.c_int}
+               "topo_sccn_combine_grid": C.c_int, "topo_hard_concrete_bwd_workspace_floats": C.c_int64,
+               "topo_layernorm_bwd_workspace_floats": C.c_int64}
 
 # unit-test / measurement entry points: only in libtopo_b200_debug.so (csrc/build.py build_debug()), never in the product library
 DEBUG_LIB_PATH = os.path.join(_HERE, "libtopo_b200_debug.so")
@@ -163,10 +166,10 @@ def _load() -> C.CDLL:
 
 # kernels launched by one call of each compute entry point (csrc/*.cu), for bench.py's gpu_launches
 KERNELS_PER_CALL = {
-    "topo_tables_face_matrix": 1, "topo_hard_concrete_fwd": 1, "topo_hard_concrete_bwd": 1,
+    "topo_tables_face_matrix": 1, "topo_hard_concrete_fwd": 1, "topo_hard_concrete_bwd": 2,
     "topo_binary_gumbel_fwd": 1, "topo_binary_gumbel_bwd": 1, "topo_rectify_fwd": 4, "topo_rectify_bwd": 4,
     "topo_active_sets": 2, "topo_penalties_fwd": 1, "topo_penalties_bwd": 1, "topo_embed_fwd": 1,
-    "topo_embed_bwd": 2, "topo_layernorm_fwd": 1, "topo_layernorm_bwd": 1, "topo_operators_count": 2,
+    "topo_embed_bwd": 2, "topo_layernorm_fwd": 1, "topo_layernorm_bwd": 2, "topo_operators_count": 2,
     "topo_operators_fill": 1, "topo_operators_bwd": 1, "topo_sccn_aggregate_fwd": 2, "topo_sccn_aggregate_bwd": 3,
     "topo_spmm_csr": 1, "topo_sddmm_csr": 1, "topo_sccn_prepare_images": 1, "topo_sccn_finish_weight_grads": 1, "topo_sccn_combine_fwd": 1, "topo_sccn_combine_fwd_tc": 1, "topo_sccn_combine_fwd_tc2": 1, "topo_sccn_combine_bwd": 2,
     "topo_sccn_combine_bwd_attention": 1, "topo_sccn_combine_bwd_conv": 1, "topo_sccn_combine_bwd_conv_tc": 1, "topo_sccn_combine_bwd_tc": 1, "topo_distance_prepare": 2,

@@ -820,7 +820,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(long long rows, cons
                                                             const float* __restrict__ gamma, float eps,
                                                             const float* __restrict__ gy_in,
                                                             float* __restrict__ gx, float* __restrict__ g_gamma,
-                                                            float* __restrict__ g_beta) {
+                                                            float* __restrict__ g_beta, float* __restrict__ cta_partials) {
     constexpr int LPR = C / 4, RPW = 32 / LPR;
     __shared__ float red[8][2][C];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sub = lane % LPR, rw = lane / LPR;
@@ -861,7 +861,8 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(long long rows, cons
                                 rstd * (gyv[2] - c1 - xh[2] * c2), rstd * (gyv[3] - c1 - xh[3] * c2));
         }
     }
-    // column sums: over the warp's row groups in shuffles, over the CTA's warps in shared memory, one atomic per column and CTA
+    // column sums: over the warp's row groups in shuffles, over the CTA's warps in shared memory, then either this CTA's slot of
+    // the partials buffer (added in CTA order by layernorm_bwd_reduce_kernel: reproducible) or one atomic per column and CTA
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
 #pragma unroll
@@ -880,7 +881,27 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(long long rows, cons
         float t = 0.f;
 #pragma unroll
         for (int w = 0; w < 8; ++w) t += red[w][which][col];
-        atomicAdd((which == 0 ? g_gamma : g_beta) + col, t);
+        if (cta_partials != nullptr) cta_partials[static_cast<size_t>(blockIdx.x) * 2 * C + idx] = t;
+        else atomicAdd((which == 0 ? g_gamma : g_beta) + col, t);
+    }
+}
+
+// g_gamma / g_beta += the CTA slots in a fixed order: thread (group, column) adds every `groups`-th slot, the groups meet in
+// shared memory in index order.  One CTA of 1024 threads.
+__global__ void __launch_bounds__(1024) layernorm_bwd_reduce_kernel(const float* __restrict__ cta_partials, int n_ctas, int c2,
+                                                                    float* __restrict__ g_gamma, float* __restrict__ g_beta) {
+    __shared__ float part[1024];
+    const int groups = 1024 / c2, grp = threadIdx.x / c2, idx = threadIdx.x % c2;
+    float t = 0.f;
+    if (grp < groups)
+        for (int b = grp; b < n_ctas; b += groups) t += cta_partials[static_cast<size_t>(b) * c2 + idx];
+    part[threadIdx.x] = t;
+    __syncthreads();
+    if (threadIdx.x < c2) {
+        float s = 0.f;
+        for (int g = 0; g < groups; ++g) s += part[g * c2 + threadIdx.x];
+        float* dst = threadIdx.x < c2 / 2 ? g_gamma + threadIdx.x : g_beta + (threadIdx.x - c2 / 2);
+        *dst += s;
     }
 }
 
@@ -1102,16 +1123,25 @@ extern "C" int topo_layernorm_fwd(int64_t rows, int channels, const float* x, co
     return TOPO_OK;
 }
 
+static int layernorm_bwd_grid(int64_t rows) { return static_cast<int>(std::min<int64_t>((rows + 7) / 8, sm_count() * 4)); }
+
+extern "C" int64_t topo_layernorm_bwd_workspace_floats(int64_t rows, int channels) {
+    if (rows < 0 || (channels != 32 && channels != 64 && channels != 128)) return -1;
+    return static_cast<int64_t>(layernorm_bwd_grid(rows)) * 2 * channels;
+}
+
 extern "C" int topo_layernorm_bwd(int64_t rows, int channels, const float* x, const float* gamma, float eps,
                                   const float* grad_y, float* grad_x, float* grad_gamma, float* grad_beta,
-                                  topo_stream_t stream) {
+                                  float* workspace, topo_stream_t stream) {
     TOPO_REQUIRE(rows >= 0 && x && gamma && grad_y && grad_x && grad_gamma && grad_beta, "bad argument");
     if (rows == 0) return TOPO_OK;
     TOPO_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(grad_y) | reinterpret_cast<uintptr_t>(grad_x) |
                    reinterpret_cast<uintptr_t>(gamma)) & 15) == 0, "buffers must be 16-byte aligned");
-    const int grid = static_cast<int>(std::min<int64_t>((rows + 7) / 8, sm_count() * 4));
+    const int grid = layernorm_bwd_grid(rows);
     DISPATCH_VEC(channels, (layernorm_bwd_kernel<VEC * 32><<<grid, 256, 0, as_stream(stream)>>>(
-                               rows, x, gamma, eps, grad_y, grad_x, grad_gamma, grad_beta)));
+                               rows, x, gamma, eps, grad_y, grad_x, grad_gamma, grad_beta, workspace)));
+    if (workspace != nullptr)
+        layernorm_bwd_reduce_kernel<<<1, 1024, 0, as_stream(stream)>>>(workspace, grid, 2 * channels, grad_gamma, grad_beta);
     TOPO_LAUNCH_CHECK();
     return TOPO_OK;
 }

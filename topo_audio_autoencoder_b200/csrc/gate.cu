@@ -80,7 +80,7 @@ template <bool TRAINING>
 __global__ void __launch_bounds__(256) hard_concrete_bwd_kernel(
     const float* __restrict__ logits, const float* __restrict__ u, const float* __restrict__ params,
     RankOffsets ro, long long total, const float* __restrict__ grad_z, float* __restrict__ grad_logits,
-    float* __restrict__ grad_params) {
+    float* __restrict__ grad_params, float* __restrict__ cta_partials) {
     const float beta = params[0], gamma = params[1], zeta = params[2];
     const float loc[4] = {params[3], params[4], params[5], params[6]};
     const long long n_cols = ro.o[4];
@@ -134,8 +134,19 @@ __global__ void __launch_bounds__(256) hard_concrete_bwd_kernel(
     if (threadIdx.x < 7) {
         float v = 0.f;
         for (int w = 0; w < (blockDim.x >> 5); ++w) v += red[w][threadIdx.x];
-        atomicAdd(&grad_params[threadIdx.x], v);
+        if (cta_partials != nullptr) cta_partials[blockIdx.x * 8 + threadIdx.x] = v;      // added in CTA order by the kernel below
+        else atomicAdd(&grad_params[threadIdx.x], v);
     }
+}
+
+// grad_params[k] = sum over the CTAs of the launch above, in a fixed order: warp k adds every 32nd slot per lane, then a shuffle tree
+__global__ void __launch_bounds__(224) hard_concrete_bwd_reduce_kernel(const float* __restrict__ cta_partials, int n_ctas,
+                                                                       float* __restrict__ grad_params) {
+    const int k = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float v = 0.f;
+    for (int b = lane; b < n_ctas; b += 32) v += cta_partials[b * 8 + k];
+    v = warp_sum(v);
+    if (lane == 0) grad_params[k] = v;
 }
 
 // BinaryGumbel training branch: softmax over the pair ([l, 1-l] + g) / T, component 0.  Written in
@@ -213,7 +224,7 @@ extern "C" int topo_hard_concrete_fwd(const float* logits, const float* u, const
 
 extern "C" int topo_hard_concrete_bwd(const float* logits, const float* u, const float* params,
                                       const int64_t offsets[5], int64_t batch, int training, const float* grad_z,
-                                      float* grad_logits, float* grad_params, topo_stream_t stream) {
+                                      float* grad_logits, float* grad_params, float* workspace, topo_stream_t stream) {
     TOPO_REQUIRE(logits && params && offsets && grad_z && grad_logits && grad_params, "null argument");
     TOPO_REQUIRE(!training || u, "u is required in training mode");
     TOPO_REQUIRE(batch >= 0 && offsets[4] > 0, "bad sizes");
@@ -227,12 +238,18 @@ extern "C" int topo_hard_concrete_bwd(const float* logits, const float* u, const
     const int grid = stream_grid((total >> 2) + 4);
     if (training)
         hard_concrete_bwd_kernel<true><<<grid, 256, 0, as_stream(stream)>>>(logits, u, params, ro, total, grad_z,
-                                                                            grad_logits, grad_params);
+                                                                            grad_logits, grad_params, workspace);
     else
         hard_concrete_bwd_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(logits, u, params, ro, total, grad_z,
-                                                                             grad_logits, grad_params);
+                                                                             grad_logits, grad_params, workspace);
+    if (workspace != nullptr) hard_concrete_bwd_reduce_kernel<<<1, 224, 0, as_stream(stream)>>>(workspace, grid, grad_params);
     TOPO_LAUNCH_CHECK();
     return TOPO_OK;
+}
+
+extern "C" int64_t topo_hard_concrete_bwd_workspace_floats(const int64_t offsets[5], int64_t batch) {
+    if (!offsets || batch < 0 || offsets[4] <= 0) return -1;
+    return 8ll * stream_grid(((batch * offsets[4]) >> 2) + 4);
 }
 
 extern "C" int topo_binary_gumbel_fwd(const float* logits, const float* gumbels, float temp, int64_t count,

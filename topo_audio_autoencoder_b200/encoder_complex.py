@@ -66,8 +66,10 @@ class _LayerNormFn(torch.autograd.Function):
         g_x = torch.empty_like(x)
         g_gamma, g_beta = torch.zeros_like(gamma), torch.zeros_like(gamma)
         g_y = g_y.contiguous()         # keep every buffer a launch reads alive in a named variable
+        # per-CTA column sums, added in CTA order: the affine gradients are bit-reproducible
+        workspace = torch.empty(int(lib.topo_layernorm_bwd_workspace_floats(x.shape[0], x.shape[1])), dtype=torch.float32, device=x.device)
         check(lib.topo_layernorm_bwd(x.shape[0], x.shape[1], ptr(x), ptr(gamma), ctx.eps, ptr(g_y),
-                                     ptr(g_x), ptr(g_gamma), ptr(g_beta), stream()))
+                                     ptr(g_x), ptr(g_gamma), ptr(g_beta), ptr(workspace), stream()))
         return g_x, g_gamma, g_beta, None
 
 

@@ -47,8 +47,12 @@ class _HardConcreteFn(torch.autograd.Function):
         grad_z = _aligned(grad_z)
         grad_logits = torch.empty_like(logits)
         grad_params = torch.empty(7, dtype=torch.float32, device=logits.device)
-        check(lib.topo_hard_concrete_bwd(ptr(logits), ptr(u), ptr(params), i64_array(ctx.offsets), ctx.batch,
-                                         int(ctx.training), ptr(grad_z), ptr(grad_logits), ptr(grad_params), stream()))
+        offsets = i64_array(ctx.offsets)
+        # per-CTA sums, added in CTA order: the seven parameter gradients are bit-reproducible
+        workspace = torch.empty(int(lib.topo_hard_concrete_bwd_workspace_floats(offsets, ctx.batch)), dtype=torch.float32,
+                                device=logits.device)
+        check(lib.topo_hard_concrete_bwd(ptr(logits), ptr(u), ptr(params), offsets, ctx.batch, int(ctx.training), ptr(grad_z),
+                                         ptr(grad_logits), ptr(grad_params), ptr(workspace), stream()))
         return grad_logits, None, grad_params, None, None, None
 
 
