@@ -37,6 +37,8 @@ namespace {
 
 using namespace tc16;
 
+constexpr bool kRowT = (TOPO_ROWMAP_TRANSPOSE & 2) != 0;
+
 constexpr int kTileRows = 128;
 constexpr int kC = 64;
 constexpr int kThreads = 512;
@@ -450,12 +452,9 @@ __global__ void __launch_bounds__(kThreads, 1) combine_bwd_fused_kernel(topo_com
                 float ga[kCW];
                 tmem_ld16(tm_ga + lane_addr + col0, ga);
                 const float sp = k == 1 ? scale_r[0] : scale_r[1];
-                if (row_alive) {
-                    float4* dst = reinterpret_cast<float4*>(G.g_agg[k - 1] + row * kC + col0);
 #pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        dst[i] = make_float4(sp * ga[4 * i], sp * ga[4 * i + 1], sp * ga[4 * i + 2], sp * ga[4 * i + 3]);
-                }
+                for (int i = 0; i < kCW; ++i) ga[i] *= sp;
+                rowmap_store16<kRowT>(G.g_agg[k - 1], row, col0, live, ga, lane);       // 64 contiguous bytes per row and access
             }
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
@@ -517,11 +516,7 @@ __global__ void __launch_bounds__(kThreads, 1) combine_bwd_fused_kernel(topo_com
                 }
                 store_split8(p_img, kPart, r, 2 * q, lo);
                 store_split8(p_img, kPart, r, 2 * q + 1, hi);
-                if (k == n_msgs - 1 && row_alive && G.g_x != nullptr) {       // g_x = sum_k dm_k is complete here
-                    float4* dxp = reinterpret_cast<float4*>(G.g_x + row * kC + col0);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) dxp[i] = make_float4(dx[4 * i], dx[4 * i + 1], dx[4 * i + 2], dx[4 * i + 3]);
-                }
+                if (k == n_msgs - 1 && G.g_x != nullptr) rowmap_store16<kRowT>(G.g_x, row, col0, live, dx, lane);   // g_x = sum_k dm_k is complete here
             }
 #pragma unroll
             for (int j = 0; j < 2; ++j) store_split8(q_img, kPart, ra + 64 * j, c, ag[j]);
@@ -555,12 +550,9 @@ __global__ void __launch_bounds__(kThreads, 1) combine_bwd_fused_kernel(topo_com
             float ga[kCW];
             tmem_ld16(tm_ga + lane_addr + col0, ga);
             const float sp = n_msgs == 1 ? scale_r[0] : (n_msgs == 2 ? scale_r[1] : scale_r[2]);
-            if (row_alive) {
-                float4* dst = reinterpret_cast<float4*>(G.g_agg[n_msgs - 1] + row * kC + col0);
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    dst[i] = make_float4(sp * ga[4 * i], sp * ga[4 * i + 1], sp * ga[4 * i + 2], sp * ga[4 * i + 3]);
-            }
+            for (int i = 0; i < kCW; ++i) ga[i] *= sp;
+            rowmap_store16<kRowT>(G.g_agg[n_msgs - 1], row, col0, live, ga, lane);
         }
         tc_fence_before_sync();
         __syncthreads();          // dy / a_k in shared memory are rewritten by the next tile's phase A

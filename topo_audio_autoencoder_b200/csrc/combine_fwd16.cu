@@ -36,6 +36,8 @@ namespace {
 
 using namespace tc16;
 
+constexpr bool kRowT = (TOPO_ROWMAP_TRANSPOSE & 1) != 0;
+
 constexpr int kTileRows = 128;
 constexpr int kC = 64;
 constexpr int kWorkers = 512;                             // 16 warps of stage / epilogue threads
@@ -299,19 +301,16 @@ __global__ void __launch_bounds__(kThreads, 1) combine_fwd16_kernel(topo_combine
     uint32_t acc0 = 0;              // accumulator of this tile's first message
     uint32_t tile_no = 0;
     float xr[kCW];                  // row map: this thread's slice of the residual row
+    float4 xraw[4];                 // the same as it arrives from global memory (64 contiguous bytes per row and access, layout.cuh)
     {
         const long long row = static_cast<long long>(blockIdx.x) * kTileRows + r;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (has_x && row < live && !(dbg & 256)) t = ldg_pinned(reinterpret_cast<const float4*>(P.x + row * kC + col0) + j);
-            xr[4 * j] = t.x; xr[4 * j + 1] = t.y; xr[4 * j + 2] = t.z; xr[4 * j + 3] = t.w;
-        }
+        rowmap_load16_issue<kRowT>(P.x, row, col0, live, has_x && !(dbg & 256), xraw, lane, [](const float4* p) { return ldg_pinned(p); });
     }
     for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++tile_no) {
         const long long row0 = tile * kTileRows;
         const long long row = row0 + r;
         const bool row_alive = row < live;
+        rowmap_load16_finish<kRowT>(xraw, xr, lane);              // issued a tile ago
         // every line this CTA reads two tiles from now goes to L2 (the register loads run up to a tile ahead)
         {
             const long long prow0 = (tile + 2 * static_cast<long long>(gridDim.x)) * kTileRows;
@@ -443,12 +442,7 @@ __global__ void __launch_bounds__(kThreads, 1) combine_fwd16_kernel(topo_combine
         // the residual slice of this CTA's next tile (in L2 since two tiles ago) travels underneath the LayerNorm
         {
             const long long nrow = (tile + gridDim.x) * kTileRows + r;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (has_x && nrow < live && !(dbg & 256)) t = ldg_pinned(reinterpret_cast<const float4*>(P.x + nrow * kC + col0) + j);
-                xr[4 * j] = t.x; xr[4 * j + 1] = t.y; xr[4 * j + 2] = t.z; xr[4 * j + 3] = t.w;
-            }
+            rowmap_load16_issue<kRowT>(P.x, nrow, col0, live, has_x && !(dbg & 256), xraw, lane, [](const float4* p) { return ldg_pinned(p); });
         }
         if (P.apply_ln) {
             // Row statistics with ONE exchange: every thread reduces its 16 columns to (sum, squared deviations from
@@ -483,11 +477,7 @@ __global__ void __launch_bounds__(kThreads, 1) combine_fwd16_kernel(topo_combine
         } else {
             named_bar_sync(3, kWorkers);                   // without the exchange: the score slots must be read by everyone
         }
-        if (row_alive && !(dbg & 32)) {
-            float4* dst = reinterpret_cast<float4*>(out + row * kC + col0);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) dst[j] = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
-        }
+        rowmap_store16<kRowT>(out, row, col0, (dbg & 32) ? 0 : live, y, lane);       // 64 contiguous bytes per row and access
         // no barrier here: the score slots are not read after the exchange above, and the statistics slots are next
         // written behind the next tile's score barrier, which no thread passes before it has read them
         acc0 += static_cast<uint32_t>(n_msgs);
