@@ -385,13 +385,15 @@ class _LayerCombineFn(torch.autograd.Function):
             off += sizes[i]
             slots = int(lib.topo_sccn_combine_grid(pr["aggs"][0].shape[0], shares[i]))
             partials.append(torch.empty(max(slots, 1) * CTA_PARTIAL_FLOATS, dtype=torch.float32, device=dev))
+        # gradient buffers of this call live in locals (not on ctx: they would stay allocated until the graph is freed)
+        g_aggs_of, g_x_of, g_x_total_of = [None] * len(ranks), [None] * len(ranks), [None] * len(ranks)
         for position, i in enumerate(order):
             pr, rc, v = per[i], ranks[i], views[i]
             rows, n = pr["aggs"][0].shape[0], rc["n_msgs"]
             g_out = g_outs[i]
             g_aggs = [torch.empty(rows, ch, dtype=torch.float32, device=dev) for _ in range(n)]
             g_x = torch.empty(rows, ch, dtype=torch.float32, device=dev) if rc["has_x"] else None
-            pr["g_aggs"], pr["g_x"] = g_aggs, g_x
+            g_aggs_of[i], g_x_of[i] = g_aggs, g_x
             if rows == 0 or g_out is None:
                 for t in g_aggs:
                     t.zero_()
@@ -448,10 +450,10 @@ class _LayerCombineFn(torch.autograd.Function):
             # place and ACCUMULATES into the residual gradients the combine kernels just wrote (no clones, no zero
             # fills, no autograd additions)
             cx = agg["cx"]
-            g_same = [per[r]["g_aggs"][0] for r in range(4)]
-            g_down = [per[r]["g_aggs"][1] for r in range(3)] + [None]
-            g_up = [None] + [per[r]["g_aggs"][2 if r < 3 else 1] for r in range(1, 4)]
-            g_x = [pr["g_x"] if pr["g_x"] is not None else torch.zeros_like(pr["xin"]) for pr in per]
+            g_same = [g_aggs_of[r][0] for r in range(4)]
+            g_down = [g_aggs_of[r][1] for r in range(3)] + [None]
+            g_up = [None] + [g_aggs_of[r][2 if r < 3 else 1] for r in range(1, 4)]
+            g_x = [g_x_of[i] if g_x_of[i] is not None else torch.zeros_like(pr["xin"]) for i, pr in enumerate(per)]
             g_probs = torch.zeros_like(agg["probs"])
             view = cx.view(agg["probs"])
             check(lib.topo_sccn_aggregate_bwd(cx.tables.handle, C.byref(view), ch, ptr_array(agg["xs"], 4),
@@ -460,8 +462,7 @@ class _LayerCombineFn(torch.autograd.Function):
                                               ptr_array(g_down, 4), ptr_array(g_up, 4), ptr_array(g_same, 4),
                                               ptr_array(g_x, 4), ptr(g_probs), stream()))
             grads_flat[0] = g_probs
-            for pr, gx in zip(per, g_x):
-                pr["g_x_total"] = gx
+            g_x_total_of = list(g_x)
             tail.join()
         # The three message scales are shared by all ranks of the layer: autograd would add up one 1-element gradient per
         # (rank, message) -- seven tiny launches per layer in the middle of the backward chain.  One product with a 0/1
@@ -479,15 +480,15 @@ class _LayerCombineFn(torch.autograd.Function):
         for i, (pr, rc) in enumerate(zip(per, ranks)):
             n, first, v = rc["n_msgs"], pr["first"], views[i]
             if agg is not None:
-                grads_flat[first] = pr["g_x_total"]
+                grads_flat[first] = g_x_total_of[i]
             elif rc["has_x"]:
-                grads_flat[first] = pr["g_x"]
+                grads_flat[first] = g_x_of[i]
             grads_flat[first + 1:first + 5] = [v["w1"], v["b1"], v["w2"], v["b2"]]
             if rc["apply_ln"]:
                 grads_flat[first + 5], grads_flat[first + 6] = v["gamma"], v["beta"]
             for k in range(n):
                 if n_agg:
-                    grads_flat[first + 7 + k] = pr["g_aggs"][k]
+                    grads_flat[first + 7 + k] = g_aggs_of[i][k]
                 grads_flat[first + 7 + n * n_agg + k] = g_w_all[q]
                 grp = owners[q]
                 if grp not in handed:
