@@ -260,7 +260,7 @@ __device__ __forceinline__ void cross_fwd_body(const DeviceTables& d, const Grou
 }
 
 template <int L, int V>
-__global__ void __launch_bounds__(kThreads) agg_cross_fwd(const DeviceTables d, const Sections sec,
+__global__ void __launch_bounds__(kThreads, 6) agg_cross_fwd(const DeviceTables d, const Sections sec,
                                                           const topo_complex_view cv, const Feat x, const FeatMut down,
                                                           const FeatMut up) {
     Group<L, V> g;
@@ -356,7 +356,7 @@ __device__ __forceinline__ void same_fwd_body(const DeviceTables& d, const Group
 }
 
 template <int L, int V>
-__global__ void __launch_bounds__(kThreads) agg_same_fwd(const DeviceTables d, const Sections sec,
+__global__ void __launch_bounds__(kThreads, 6) agg_same_fwd(const DeviceTables d, const Sections sec,
                                                          const topo_complex_view cv, const Feat x, const Feat down,
                                                          const Feat up, const FeatMut same) {
     Group<L, V> g;
