@@ -88,26 +88,40 @@ __global__ void __launch_bounds__(1024) finish_weight_grads_kernel(const __grid_
         n_active = static_cast<int>(min(tiles, min(launched, static_cast<long long>(cap))));
     }
     float acc = 0.f;
-    for (int i0 = 0; i0 < n; i0 += 256) {
-        const int i = i0 + e;
-        float p = 0.f;
+    // 16 chunks of 256 elements at a time: every thread keeps 16 independent loads per CTA slot in flight (one chunk at a time the
+    // kernel was a chain of slot loads: 84 us for a 64 x 64 matrix over 107 slots).  The order of every sum is unchanged.
+    for (int i00 = 0; i00 < n; i00 += 16 * 256) {
+        float t[16];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) t[c] = 0.f;
         if (job.partials != nullptr) {
-            float t = 0.f;
-            if (i < n) {
-                const float* src = job.partials + job.partial_offset + i;
-#pragma unroll 4
-                for (int b = qd; b < n_active; b += 4) t += __ldcs(src + static_cast<size_t>(b) * kCtaPartialFloats);
+            const float* src = job.partials + job.partial_offset + i00 + e;
+            for (int b = qd; b < n_active; b += 4) {
+                const float* sb = src + static_cast<size_t>(b) * kCtaPartialFloats;
+#pragma unroll
+                for (int c = 0; c < 16; ++c)
+                    if (i00 + c * 256 + e < n) t[c] += __ldcs(sb + c * 256);
             }
-            quarter[qd][e] = t;
-            __syncthreads();
-            p = (quarter[0][e] + quarter[1][e]) + (quarter[2][e] + quarter[3][e]);
-            __syncthreads();
-        } else if (i < n) {
-            p = job.wprod[i];
         }
-        if (qd == 0 && i < n) {
-            job.g_w[i] = s * p;
-            if (conv) acc = fmaf(p, __ldg(job.w + i), acc);
+#pragma unroll 1
+        for (int c = 0; c < 16 && i00 + c * 256 < n; ++c) {
+            const int i = i00 + c * 256 + e;
+            float p = 0.f;
+            if (job.partials != nullptr) {
+                float tc = 0.f;      // select instead of t[c]: a runtime index would move the array to local memory
+#pragma unroll
+                for (int cc = 0; cc < 16; ++cc) tc = cc == c ? t[cc] : tc;
+                quarter[qd][e] = tc;
+                __syncthreads();
+                p = (quarter[0][e] + quarter[1][e]) + (quarter[2][e] + quarter[3][e]);
+                __syncthreads();
+            } else if (i < n) {
+                p = job.wprod[i];
+            }
+            if (qd == 0 && i < n) {
+                job.g_w[i] = s * p;
+                if (conv) acc = fmaf(p, __ldg(job.w + i), acc);
+            }
         }
     }
     if (!conv) return;
