@@ -122,6 +122,38 @@ def test_tile_fragment_layout_is_a_permutation_of_each_tile():
     assert (seen == 1).all()
 
 
+def test_row_map_lane_transpose_is_an_involution_with_the_documented_access_pattern():
+    """layout.cuh rowmap_transpose4: two butterfly steps over every group of four lanes.  Mirrors the device function on a
+    [32 lanes][4 slots] table of (row, chunk) labels: afterwards lane 4g + j holds chunk j of rows 4g .. 4g + 3 in slot order
+    (so access number i of a warp touches 64 contiguous bytes of rows 4g + i), and applying it twice is the identity."""
+    def transpose4(v):            # v[lane][slot]
+        v = [list(lane) for lane in v]
+        for dist_, pairs in ((2, ((0, 2), (1, 3))), (1, ((0, 1), (2, 3)))):
+            for lo, hi_slot in pairs:
+                send = [v[l][lo] if (l & dist_) else v[l][hi_slot] for l in range(32)]     # what every lane hands over
+                recv = [send[l ^ dist_] for l in range(32)]                                 # __shfl_xor_sync
+                for l in range(32):
+                    if l & dist_:
+                        v[l][lo] = recv[l]
+                    else:
+                        v[l][hi_slot] = recv[l]
+        return v
+
+    start = [[(lane, chunk) for chunk in range(4)] for lane in range(32)]      # row map: lane l holds chunks 0..3 of row l
+    t = transpose4(start)
+    for lane in range(32):
+        g, j = lane // 4, lane % 4
+        assert t[lane] == [(4 * g + i, j) for i in range(4)]
+    assert transpose4(t) == start
+    # one warp access i: the bytes each row receives are one contiguous 64-byte run (chunks 0..3 of 16 bytes)
+    for i in range(4):
+        by_row = {}
+        for lane in range(32):
+            row, chunk = t[lane][i]
+            by_row.setdefault(row, []).append(chunk)
+        assert len(by_row) == 8 and all(sorted(c) == [0, 1, 2, 3] for c in by_row.values())
+
+
 def _gather_topk_worker(rank, world, port, q):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
