@@ -1,4 +1,5 @@
-"""What do the aggregation launches cost when no row is alive (grids are sized by the bound B * n_r)?  And with every row alive?
+"""(Rewritten to time a CUDA-graph replay after the eager version turned out to measure the host launch path; this form has not
+been run on a GPU yet.)  What do the aggregation launches cost when no row is alive (grids are sized by the bound B * n_r)?  And with every row alive?
 Times topo_sccn_aggregate_fwd / _bwd on a batch of 64 complexes: all simplices inactive, ~35 % active (random), all active."""
 import os, sys, ctypes as C
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
